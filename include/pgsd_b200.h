@@ -1,0 +1,157 @@
+/* pgsd_b200.h -- B200 extensions of the PGSD C ABI (libpgsd_b200.so).
+ *
+ * Everything the reference gets from MPI or does on the host around its hot path, and
+ * that has no slot in pgsd.h, enters here: the rank communicator, device-resident SoA
+ * chunk writes (K1), the size allgather + exclusive scan (K2), and the particle-id
+ * reorder of a decoded frame (K4 radix sort + K5 gather).  Plain pointers and sizes
+ * only; no torch / numpy / MPI types.  Each entry cites the reference code it replaces
+ * (paths relative to /root/reference/).
+ */
+#ifndef PGSD_B200_EXT_H
+#define PGSD_B200_EXT_H
+
+#include "pgsd.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ communicator
+ * Replaces MPI_Init + MPI_COMM_WORLD (ref: pgsd.c:1487-1488 caches rank/nprocs; the
+ * benchmarks call MPI_Init, benchmark-write.cc:23).  One process per GPU.  Exactly one
+ * transport is active per process; pgsd_open/pgsd_create_and_open capture it.
+ *   nccl : sizes are all-gathered with ncclAllGather over NVLink and scanned on the
+ *          device (K2).  This is the production transport.
+ *   host : the caller supplies an all-gather of uint64 vectors (e.g. gloo / an MPI the
+ *          host application already has); used for host-pointer-only operation and for
+ *          the CPU test-suite.
+ *   shm  : built-in single-host transport over a POSIX shared-memory segment.
+ */
+typedef int (*pgsd_b200_allgather_fn)(void* ctx, const uint64_t* send, uint64_t* recv,
+                                      size_t n_per_rank);
+
+int pgsd_b200_comm_init_host(int rank, int nprocs, pgsd_b200_allgather_fn fn, void* ctx);
+int pgsd_b200_comm_init_shm(int rank, int nprocs, const char* segment_name);
+/* fills 128 bytes; call on rank 0 and ship the bytes to the other ranks out of band */
+int pgsd_b200_nccl_unique_id(void* out128);
+int pgsd_b200_comm_init_nccl(int rank, int nprocs, const void* unique_id128, int cuda_device);
+int pgsd_b200_comm_finalize(void);
+int pgsd_b200_comm_rank(void);
+int pgsd_b200_comm_size(void);
+const char* pgsd_b200_comm_kind(void); /* "single" | "host" | "shm" | "nccl" */
+int pgsd_b200_barrier(void);
+
+/* Caller-side partition offsets: all-gather n_local over the ranks, return the global
+   row count and this rank's exclusive prefix.  Replaces the MPI_Allgather + prefix loop
+   every multi-rank caller of the reference writes by hand
+   (ref: benchmark-write.cc:33-45, benchmark-read.cc:64-76, fl.pyx:596-598). */
+int pgsd_b200_partition(uint64_t n_local, uint64_t* n_global, uint64_t* row_start);
+
+/* ------------------------------------------------------------------ device
+ * CUDA state is created lazily by the first call that needs it. */
+int pgsd_b200_cuda_available(void);     /* 1 if a CUDA device can be used */
+int pgsd_b200_device_init(int cuda_device);
+/* Stream on which the caller produces device data; K1 pack kernels are launched on it
+   so that "data may be reused as soon as the call returns" holds in stream order
+   (ref semantics: pgsd.c:521, :2229 finish with the caller's buffer before returning). */
+int pgsd_b200_set_stream(void* cuda_stream);
+const char* pgsd_b200_last_error(void);
+
+/* pinned staging ring used between the device arena and pwrite (K3);
+   defaults: 8 slots x 16 MiB, 8 writer threads.  Call before the first device write. */
+int pgsd_b200_configure_staging(uint32_t n_slots, uint64_t slot_bytes, uint32_t writer_threads);
+
+/* Use as `offset` to let the library place this rank's slice at the exclusive prefix
+   (over ranks) of N*M elements, computed by K2 at frame commit. */
+#define PGSD_B200_OFFSET_AUTO UINT64_MAX
+
+/* One source column of a chunk: element j of row i is read from
+   ((const src_type*)base)[i * stride].  SoA: M columns with stride 1.  AoS (e.g. HOOMD's
+   Scalar4 pos): M columns base+j with stride 4.  Already packed (N,M): base+j, stride M. */
+struct pgsd_b200_column
+    {
+    const void* base;
+    int64_t stride; /* in elements of src_type */
+    };
+
+/* K1 -- pgsd_write_chunk for a chunk that still has to be packed and dtype-cast:
+   dst[i*M + j] = (dst_type) cols[j][i*stride_j].  Columns are CUDA device pointers (hot
+   path) or host pointers (copied host->device through the pinned ring first).
+   Replaces the host cast + contiguity copy in front of the reference's write
+   (ref: fl.pyx:571 numpy.ascontiguousarray, hoomd.py:206-270 ParticleData.validate)
+   followed by pgsd_write_chunk (pgsd.c:2072-2259).  Same return codes as
+   pgsd_write_chunk; unsupported casts (float -> integer) return INVALID_ARGUMENT. */
+int pgsd_b200_write_chunk_soa(struct pgsd_handle* handle,
+                              const char* name,
+                              enum pgsd_type dst_type,
+                              uint64_t N,
+                              uint32_t M,
+                              uint64_t N_global,
+                              uint32_t M_global,
+                              uint64_t offset,
+                              bool all,
+                              enum pgsd_type src_type,
+                              const struct pgsd_b200_column* cols);
+
+/* K1 alone: pack device columns into a device buffer on `cuda_stream` (no file). */
+int pgsd_b200_pack_soa(void* dst_device,
+                       enum pgsd_type dst_type,
+                       uint64_t N,
+                       uint32_t M,
+                       enum pgsd_type src_type,
+                       const struct pgsd_b200_column* cols_device,
+                       void* cuda_stream);
+
+/* K2 alone: sizes[P][C] (host) -> per chunk: exclusive prefix over ranks < rank, sum and
+   max over ranks, computed by the device scan kernel.
+   Replaces pgsd.c:1126 + :1150-1152 (Allgather + prefix), :1162/:2242 (SUM), :2157 (MAX). */
+int pgsd_b200_scan_sizes(const uint64_t* sizes, int P, int C, int rank,
+                         uint64_t* excl, uint64_t* total, uint64_t* maxv);
+
+/* ------------------------------------------------------------------ reorder (K4 + K5)
+ * Oracle definition (BASELINE.json north_star): o = numpy.argsort(keys, kind='stable');
+ * out_f = in_f[o] for every field.  Bit-exact: payload is moved, never computed on. */
+struct pgsd_b200_field
+    {
+    const void* in;     /* n rows of row_bytes */
+    void* out;          /* n rows of row_bytes, must not alias in */
+    uint32_t row_bytes; /* 1..64, e.g. 12 for an (N,3) float32 field */
+    };
+
+/* K4: stable LSD radix sort of (key, original index) pairs on the device.
+   keys_sorted and perm may be NULL if not wanted. */
+int pgsd_b200_sort_ids(uint64_t n, const uint32_t* keys_device, uint32_t* keys_sorted_device,
+                       uint32_t* perm_device, void* cuda_stream);
+
+/* K5: out_f[i] = in_f[perm[i]] for all fields in one launch. */
+int pgsd_b200_gather(uint64_t n, const uint32_t* perm_device, int nfields,
+                     const struct pgsd_b200_field* fields_device, void* cuda_stream);
+
+/* K4+K5 on device-resident data. */
+int pgsd_b200_reorder_device(uint64_t n, const uint32_t* keys_device, uint32_t* keys_sorted_device,
+                             uint32_t* perm_device, int nfields,
+                             const struct pgsd_b200_field* fields_device, void* cuda_stream);
+
+/* Host buffers in, host buffers out: pinned H2D, K4+K5, pinned D2H inside the call. */
+int pgsd_b200_reorder_host(uint64_t n, const uint32_t* keys_host, uint32_t* keys_sorted_host,
+                           uint32_t* perm_host, int nfields,
+                           const struct pgsd_b200_field* fields_host);
+
+/* ------------------------------------------------------------------ accounting */
+struct pgsd_b200_stats
+    {
+    uint64_t kernel_launches; /* CUDA kernels launched by this library */
+    uint64_t h2d_bytes;
+    uint64_t d2h_bytes;
+    uint64_t file_bytes_written;
+    uint64_t file_bytes_read;
+    uint64_t collectives; /* all-gathers issued through the communicator */
+    double commit_wait_s; /* host time blocked in frame commits (D2H + pwrite drain) */
+    };
+int pgsd_b200_get_stats(struct pgsd_b200_stats* out);
+int pgsd_b200_reset_stats(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PGSD_B200_EXT_H */

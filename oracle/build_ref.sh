@@ -1,0 +1,21 @@
+#!/bin/bash
+# Build the UNMODIFIED reference libpgsd (C) in place from /root/reference into oracle/_ref/.
+# TEST INFRASTRUCTURE ONLY: outputs are git-ignored binaries used as the parity checker and
+# as bench.py's CPU "reference" arm.  No reference source is copied into this repository.
+# /root/reference does not exist on the GPU box: there the prebuilt oracle/_ref/ files are used.
+set -euo pipefail
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+REF="${PGSD_REFERENCE_ROOT:-/root/reference}/pgsd/pgsd"
+OUT="$HERE/_ref"
+if [ ! -f "$REF/pgsd.c" ]; then
+    echo "build_ref.sh: $REF/pgsd.c not found (expected on the GPU box); keeping prebuilt $OUT" >&2
+    exit 0
+fi
+mkdir -p "$OUT"
+CFLAGS="-O2 -g -fPIC -w -I$HERE/shim -I$REF"
+gcc $CFLAGS -c "$REF/pgsd.c" -o "$OUT/pgsd_ref.o"
+gcc $CFLAGS -c "$HERE/shim/mpishim.c" -o "$OUT/mpishim.o"
+gcc $CFLAGS -c "$HERE/ref_driver.c" -o "$OUT/ref_driver.o"
+gcc -o "$OUT/ref_driver" "$OUT/ref_driver.o" "$OUT/pgsd_ref.o" "$OUT/mpishim.o" -lpthread -lm
+gcc -shared -o "$OUT/libpgsd_ref.so" "$OUT/pgsd_ref.o" "$OUT/mpishim.o" -lpthread
+echo "built $OUT/ref_driver and $OUT/libpgsd_ref.so from $REF/pgsd.c"

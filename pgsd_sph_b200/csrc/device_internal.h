@@ -1,0 +1,46 @@
+// device_internal.h -- shared by the .cu translation units of libpgsd_b200 only.
+#pragma once
+#include "device.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstring>
+#include <string>
+
+namespace pgsdb
+{
+int dev_sm_count();               // valid after dev_init()
+void sort_release_workspace();    // kernels_sort.cu
+
+// pgsd_type codes (include/pgsd.h; ref: /root/reference/pgsd/pgsd/pgsd.h:38-69)
+enum : int
+    {
+    T_U8 = 1,
+    T_U16 = 2,
+    T_U32 = 3,
+    T_U64 = 4,
+    T_I8 = 5,
+    T_I16 = 6,
+    T_I32 = 7,
+    T_I64 = 8,
+    T_F32 = 9,
+    T_F64 = 10
+    };
+
+// ---- K1 launch interface (kernels_pack.cu)
+constexpr int PACK_MAX_COLS = 8;
+constexpr int PACK_MAX_SEGS = 16;
+struct PackSegment
+    {
+    void* dst;                          // packed (N, M) array of dst_type, device
+    const void* base[PACK_MAX_COLS];    // device column bases
+    long long stride[PACK_MAX_COLS];    // in elements of src_type
+    unsigned long long N;
+    unsigned int M;
+    int src_type;
+    int dst_type;
+    };
+// one launch packs all segments (the chunks of one frame)
+int pack_launch(const PackSegment* segs, int nsegs, cudaStream_t st);
+} // namespace pgsdb
