@@ -151,6 +151,25 @@ struct pgsd_b200_stats
 int pgsd_b200_get_stats(struct pgsd_b200_stats* out);
 int pgsd_b200_reset_stats(void);
 
+/* ------------------------------------------------------------------ raw device helpers
+ * For host layers without a CUDA runtime of their own (the Python file layer, the replay tool,
+ * bench.py): device / pinned allocation, synchronous copies (kind: 1 H2D, 2 D2H, 3 D2D),
+ * CUDA-event timers on the stream set with pgsd_b200_set_stream, and an L2 flush (writes a
+ * 256 MiB buffer).  pgsd_b200_drain waits for every queued file write of this rank. */
+int pgsd_b200_malloc(void** p, uint64_t bytes);
+int pgsd_b200_free(void* p);
+int pgsd_b200_host_alloc(void** p, uint64_t bytes);
+int pgsd_b200_host_free(void* p);
+int pgsd_b200_memcpy(void* dst, const void* src, uint64_t bytes, int kind);
+int pgsd_b200_synchronize(void);
+int pgsd_b200_drain(void);
+int pgsd_b200_shutdown(void);
+int pgsd_b200_timer_create(void** t);
+int pgsd_b200_timer_start(void* t);
+int pgsd_b200_timer_stop(void* t, float* ms);
+int pgsd_b200_timer_destroy(void* t);
+int pgsd_b200_flush_l2(void);
+
 #ifdef __cplusplus
 }
 #endif

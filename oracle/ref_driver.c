@@ -304,7 +304,16 @@ static int run_script(const char* ops_path, const char* blob_path, const char* o
             char prefix[4096];
             sscanf(rest, "%4095s", prefix);
             const char* m = strcmp(prefix, "-") ? prefix : "";
-            const char* found = pgsd_find_matching_chunk_name(&h, m, NULL);
+            /* Non-root ranks hold no namelist (pgsd.c:1531-1607) and would dereference NULL
+               (pgsd.c:2590), so only root may call; on a writable file the call flushes
+               collectively (pgsd.c:2579-2586), which root cannot do alone: unsupported at P > 1. */
+            if (g_np > 1 && h.open_flags != PGSD_OPEN_READONLY)
+                {
+                if (log)
+                    fprintf(log, "%d match unsupported\n", opno);
+                continue;
+                }
+            const char* found = g_rank == 0 ? pgsd_find_matching_chunk_name(&h, m, NULL) : NULL;
             if (log)
                 fprintf(log, "%d match", opno);
             while (g_rank == 0 && found)

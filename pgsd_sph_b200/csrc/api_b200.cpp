@@ -1,0 +1,291 @@
+// api_b200.cpp -- the pgsd_b200.h C ABI: communicator set-up, device-resident SoA chunk writes
+// (K1), the size scan (K2), the particle-id reorder (K4 + K5) and accounting.  Thin extern "C"
+// shims over comm.cpp / device.cu / kernels_*.cu / pgsd_file.cpp; no CUDA or torch types cross.
+#include "../../include/pgsd_b200.h"
+#include "comm.h"
+#include "device.h"
+#include "file_internal.h"
+
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace pgsdb;
+
+extern "C" {
+
+// ------------------------------------------------------------------ communicator
+int pgsd_b200_comm_init_host(int rank, int nprocs, pgsd_b200_allgather_fn fn, void* ctx)
+    {
+    if (nprocs < 1 || rank < 0 || rank >= nprocs || (nprocs > 1 && fn == nullptr))
+        {
+        set_last_error("comm_init_host: bad rank/nprocs or missing all-gather callback");
+        return PGSD_ERROR_INVALID_ARGUMENT;
+        }
+    comm_replace(nprocs == 1 ? nullptr : make_host_comm(rank, nprocs, fn, ctx));
+    return PGSD_SUCCESS;
+    }
+
+int pgsd_b200_comm_init_shm(int rank, int nprocs, const char* segment_name)
+    {
+    if (nprocs < 1 || rank < 0 || rank >= nprocs || segment_name == nullptr)
+        {
+        set_last_error("comm_init_shm: bad rank/nprocs/name");
+        return PGSD_ERROR_INVALID_ARGUMENT;
+        }
+    if (nprocs == 1)
+        {
+        comm_replace(nullptr);
+        return PGSD_SUCCESS;
+        }
+    std::string err;
+    Comm* c = make_shm_comm(rank, nprocs, segment_name, err);
+    if (!c)
+        {
+        set_last_error(err);
+        return PGSD_ERROR_IO;
+        }
+    comm_replace(c);
+    return PGSD_SUCCESS;
+    }
+
+int pgsd_b200_nccl_unique_id(void* out128)
+    {
+    if (out128 == nullptr)
+        return PGSD_ERROR_INVALID_ARGUMENT;
+    std::string err;
+    if (nccl_unique_id(out128, err) != 0)
+        {
+        set_last_error(err);
+        return PGSD_ERROR_IO;
+        }
+    return PGSD_SUCCESS;
+    }
+
+int pgsd_b200_comm_init_nccl(int rank, int nprocs, const void* unique_id128, int cuda_device)
+    {
+    if (nprocs < 1 || rank < 0 || rank >= nprocs || unique_id128 == nullptr)
+        {
+        set_last_error("comm_init_nccl: bad rank/nprocs/id");
+        return PGSD_ERROR_INVALID_ARGUMENT;
+        }
+    std::string err;
+    Comm* c = make_nccl_comm(rank, nprocs, unique_id128, cuda_device, err);
+    if (!c)
+        {
+        set_last_error(err);
+        return PGSD_ERROR_IO;
+        }
+    comm_replace(c);
+    return PGSD_SUCCESS;
+    }
+
+int pgsd_b200_comm_finalize(void)
+    {
+    comm_replace(nullptr);
+    return PGSD_SUCCESS;
+    }
+
+int pgsd_b200_comm_rank(void) { return comm()->rank; }
+int pgsd_b200_comm_size(void) { return comm()->nprocs; }
+const char* pgsd_b200_comm_kind(void) { return comm_kind_name(); }
+int pgsd_b200_barrier(void) { return comm()->barrier() == 0 ? PGSD_SUCCESS : PGSD_ERROR_IO; }
+
+int pgsd_b200_partition(uint64_t n_local, uint64_t* n_global, uint64_t* row_start)
+    {
+    SizeScan sc;
+    if (comm()->allgather_scan(&n_local, &sc, 1) != 0)
+        return PGSD_ERROR_IO;
+    if (n_global)
+        *n_global = sc.total;
+    if (row_start)
+        *row_start = sc.excl;
+    return PGSD_SUCCESS;
+    }
+
+// ------------------------------------------------------------------ device
+int pgsd_b200_cuda_available(void) { return dev_cuda_available() ? 1 : 0; }
+int pgsd_b200_device_init(int cuda_device) { return dev_init(cuda_device); }
+int pgsd_b200_set_stream(void* cuda_stream)
+    {
+    dev_set_user_stream(cuda_stream);
+    return PGSD_SUCCESS;
+    }
+const char* pgsd_b200_last_error(void) { return last_error().c_str(); }
+
+int pgsd_b200_configure_staging(uint32_t n_slots, uint64_t slot_bytes, uint32_t writer_threads)
+    {
+    return dev_configure_staging(n_slots, slot_bytes, writer_threads);
+    }
+
+static bool columns_on_device(const struct pgsd_b200_column* cols, uint32_t M, bool* mixed)
+    {
+    int ndev = 0;
+    for (uint32_t j = 0; j < M; j++)
+        if (dev_is_device_pointer(cols[j].base))
+            ndev++;
+    *mixed = ndev != 0 && ndev != (int)M;
+    return ndev == (int)M;
+    }
+
+int pgsd_b200_write_chunk_soa(struct pgsd_handle* handle, const char* name, enum pgsd_type dst_type,
+                              uint64_t N, uint32_t M, uint64_t N_global, uint32_t M_global,
+                              uint64_t offset, bool all, enum pgsd_type src_type,
+                              const struct pgsd_b200_column* cols)
+    {
+    if (M == 0 || M > 8 || (N > 0 && cols == nullptr))
+        return PGSD_ERROR_INVALID_ARGUMENT;
+    Column c[8];
+    bool on_device = true, mixed = false;
+    if (N > 0)
+        {
+        for (uint32_t j = 0; j < M; j++)
+            {
+            if (cols[j].base == nullptr)
+                return PGSD_ERROR_INVALID_ARGUMENT;
+            c[j].base = cols[j].base;
+            c[j].stride = cols[j].stride;
+            }
+        on_device = columns_on_device(cols, M, &mixed);
+        if (mixed)
+            {
+            set_last_error("write_chunk_soa: columns must be all device or all host pointers");
+            return PGSD_ERROR_INVALID_ARGUMENT;
+            }
+        }
+    return file_write_chunk_device(handle, name, (int)dst_type, N, M, N_global, M_global, offset, all,
+                                   (int)src_type, c, !on_device);
+    }
+
+int pgsd_b200_pack_soa(void* dst_device, enum pgsd_type dst_type, uint64_t N, uint32_t M,
+                       enum pgsd_type src_type, const struct pgsd_b200_column* cols_device,
+                       void* cuda_stream)
+    {
+    if (M == 0 || M > 8 || cols_device == nullptr)
+        return PGSD_ERROR_INVALID_ARGUMENT;
+    Column c[8];
+    for (uint32_t j = 0; j < M; j++)
+        {
+        c[j].base = cols_device[j].base;
+        c[j].stride = cols_device[j].stride;
+        }
+    return dev_pack(dst_device, (int)dst_type, N, M, (int)src_type, c, cuda_stream);
+    }
+
+int pgsd_b200_scan_sizes(const uint64_t* sizes, int P, int C, int rank, uint64_t* excl,
+                         uint64_t* total, uint64_t* maxv)
+    {
+    if (C < 0)
+        return PGSD_ERROR_INVALID_ARGUMENT;
+    std::vector<SizeScan> out((size_t)C);
+    int rc = dev_scan_sizes(sizes, P, C, rank, out.data());
+    if (rc != 0)
+        return rc;
+    for (int c = 0; c < C; c++)
+        {
+        if (excl)
+            excl[c] = out[(size_t)c].excl;
+        if (total)
+            total[c] = out[(size_t)c].total;
+        if (maxv)
+            maxv[c] = out[(size_t)c].maxv;
+        }
+    return PGSD_SUCCESS;
+    }
+
+// ------------------------------------------------------------------ reorder
+static int to_fields(int nfields, const struct pgsd_b200_field* in, std::vector<ReorderField>& out)
+    {
+    if (nfields < 0 || (nfields > 0 && in == nullptr))
+        return PGSD_ERROR_INVALID_ARGUMENT;
+    out.resize((size_t)nfields);
+    for (int i = 0; i < nfields; i++)
+        {
+        out[(size_t)i].in = in[i].in;
+        out[(size_t)i].out = in[i].out;
+        out[(size_t)i].row_bytes = in[i].row_bytes;
+        }
+    return PGSD_SUCCESS;
+    }
+
+int pgsd_b200_sort_ids(uint64_t n, const uint32_t* keys_device, uint32_t* keys_sorted_device,
+                       uint32_t* perm_device, void* cuda_stream)
+    {
+    return dev_sort_ids(n, keys_device, keys_sorted_device, perm_device, cuda_stream);
+    }
+
+int pgsd_b200_gather(uint64_t n, const uint32_t* perm_device, int nfields,
+                     const struct pgsd_b200_field* fields_device, void* cuda_stream)
+    {
+    std::vector<ReorderField> f;
+    int rc = to_fields(nfields, fields_device, f);
+    if (rc != 0)
+        return rc;
+    return dev_gather(n, perm_device, nfields, f.data(), cuda_stream);
+    }
+
+int pgsd_b200_reorder_device(uint64_t n, const uint32_t* keys_device, uint32_t* keys_sorted_device,
+                             uint32_t* perm_device, int nfields,
+                             const struct pgsd_b200_field* fields_device, void* cuda_stream)
+    {
+    std::vector<ReorderField> f;
+    int rc = to_fields(nfields, fields_device, f);
+    if (rc != 0)
+        return rc;
+    return dev_reorder(n, keys_device, keys_sorted_device, perm_device, nfields, f.data(), cuda_stream);
+    }
+
+int pgsd_b200_reorder_host(uint64_t n, const uint32_t* keys_host, uint32_t* keys_sorted_host,
+                           uint32_t* perm_host, int nfields, const struct pgsd_b200_field* fields_host)
+    {
+    std::vector<ReorderField> f;
+    int rc = to_fields(nfields, fields_host, f);
+    if (rc != 0)
+        return rc;
+    return dev_reorder_host(n, keys_host, keys_sorted_host, perm_host, nfields, f.data());
+    }
+
+// ------------------------------------------------------------------ accounting
+int pgsd_b200_get_stats(struct pgsd_b200_stats* out)
+    {
+    if (out == nullptr)
+        return PGSD_ERROR_INVALID_ARGUMENT;
+    const DevStats& s = dev_stats();
+    out->kernel_launches = s.kernel_launches;
+    out->h2d_bytes = s.h2d_bytes;
+    out->d2h_bytes = s.d2h_bytes;
+    out->file_bytes_written = s.file_bytes_written;
+    out->file_bytes_read = s.file_bytes_read;
+    out->collectives = g_collectives;
+    out->commit_wait_s = s.commit_wait_s;
+    return PGSD_SUCCESS;
+    }
+
+int pgsd_b200_reset_stats(void)
+    {
+    dev_stats() = DevStats();
+    g_collectives = 0;
+    return PGSD_SUCCESS;
+    }
+
+// ------------------------------------------------------------------ raw device helpers
+// For callers without a CUDA runtime of their own (the ctypes host layer, the replay tool, bench.py).
+int pgsd_b200_malloc(void** p, uint64_t bytes) { return dev_malloc(p, bytes); }
+int pgsd_b200_free(void* p) { return dev_free(p); }
+int pgsd_b200_host_alloc(void** p, uint64_t bytes) { return dev_host_alloc(p, bytes); }
+int pgsd_b200_host_free(void* p) { return dev_host_free(p); }
+int pgsd_b200_memcpy(void* dst, const void* src, uint64_t bytes, int kind) { return dev_memcpy(dst, src, bytes, kind); }
+int pgsd_b200_synchronize(void) { return dev_synchronize(); }
+int pgsd_b200_drain(void) { return dev_drain(); }
+int pgsd_b200_shutdown(void)
+    {
+    dev_shutdown();
+    return PGSD_SUCCESS;
+    }
+int pgsd_b200_timer_create(void** t) { return dev_timer_create(t); }
+int pgsd_b200_timer_start(void* t) { return dev_timer_start(t); }
+int pgsd_b200_timer_stop(void* t, float* ms) { return dev_timer_stop(t, ms); }
+int pgsd_b200_timer_destroy(void* t) { return dev_timer_destroy(t); }
+int pgsd_b200_flush_l2(void) { return dev_flush_l2(); }
+
+} // extern "C"

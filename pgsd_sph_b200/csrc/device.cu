@@ -950,6 +950,30 @@ Comm* make_nccl_comm(int rank, int nprocs, const void* unique_id, int device, st
     return c;
     }
 
+// ------------------------------------------------------------------------------ reorder (K4 + K5)
+int dev_reorder(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, uint32_t* perm, int nfields,
+                const ReorderField* fields, void* stream)
+    {
+    int rc = dev_init(-1);
+    if (rc != 0)
+        return rc;
+    if (n == 0)
+        return 0;
+    uint32_t* p = perm;
+    if (p == nullptr)
+        {
+        // the permutation is needed even when the caller does not want it back
+        rc = scratch_reserve((size_t)n * 4);
+        if (rc != 0)
+            return rc;
+        p = (uint32_t*)g.scratch;
+        }
+    rc = dev_sort_ids(n, keys, keys_sorted, p, stream);
+    if (rc != 0)
+        return rc;
+    return dev_gather(n, p, nfields, fields, stream);
+    }
+
 // ------------------------------------------------------------------------------ reorder, host buffers
 int dev_reorder_host(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, uint32_t* perm, int nfields,
                      const ReorderField* fields)

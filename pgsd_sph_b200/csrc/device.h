@@ -92,6 +92,8 @@ int dev_sort_ids(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, uint32
                  void* stream);
 int dev_gather(uint64_t n, const uint32_t* perm, int nfields, const ReorderField* fields,
                void* stream);
+int dev_reorder(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, uint32_t* perm, int nfields,
+                const ReorderField* fields, void* stream);
 int dev_reorder_host(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, uint32_t* perm,
                      int nfields, const ReorderField* fields);
 
