@@ -93,6 +93,24 @@ int pgsd_b200_write_chunk_soa(struct pgsd_handle* handle,
                               enum pgsd_type src_type,
                               const struct pgsd_b200_column* cols);
 
+/* A whole frame's SoA chunks in one call: ONE K1 launch packs all of them (<= 16 per launch),
+   then each is recorded exactly as pgsd_b200_write_chunk_soa would, in array order. */
+struct pgsd_b200_chunk_desc
+    {
+    const char* name;
+    enum pgsd_type dst_type;
+    enum pgsd_type src_type;
+    uint64_t N;
+    uint32_t M;
+    uint64_t N_global; /* UINT64_MAX: let the library sum N over the ranks at frame commit */
+    uint32_t M_global;
+    uint64_t offset; /* elements, or PGSD_B200_OFFSET_AUTO */
+    bool all;
+    const struct pgsd_b200_column* cols; /* M columns, all device or all host */
+    };
+int pgsd_b200_write_chunks_soa(struct pgsd_handle* handle, int n_chunks,
+                               const struct pgsd_b200_chunk_desc* chunks);
+
 /* K1 alone: pack device columns into a device buffer on `cuda_stream` (no file). */
 int pgsd_b200_pack_soa(void* dst_device,
                        enum pgsd_type dst_type,

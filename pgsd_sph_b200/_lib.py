@@ -108,6 +108,12 @@ class Column(C.Structure):  # struct pgsd_b200_column
     _fields_ = [("base", C.c_void_p), ("stride", C.c_int64)]
 
 
+class ChunkDesc(C.Structure):  # struct pgsd_b200_chunk_desc
+    _fields_ = [("name", C.c_char_p), ("dst_type", C.c_int), ("src_type", C.c_int), ("N", C.c_uint64),
+                ("M", C.c_uint32), ("N_global", C.c_uint64), ("M_global", C.c_uint32), ("offset", C.c_uint64),
+                ("all", C.c_bool), ("cols", C.POINTER(Column))]
+
+
 class Field(C.Structure):  # struct pgsd_b200_field
     _fields_ = [("in_", C.c_void_p), ("out", C.c_void_p), ("row_bytes", C.c_uint32)]
 
@@ -163,6 +169,7 @@ SIGNATURES = {
     "pgsd_b200_last_error": (C.c_char_p, []),
     "pgsd_b200_configure_staging": (_i, [_u32, _u64, _u32]),
     "pgsd_b200_write_chunk_soa": (_i, [_HP, C.c_char_p, _i, _u64, _u32, _u64, _u32, _u64, C.c_bool, _i, C.POINTER(Column)]),
+    "pgsd_b200_write_chunks_soa": (_i, [_HP, _i, C.POINTER(ChunkDesc)]),
     "pgsd_b200_pack_soa": (_i, [_vp, _i, _u64, _u32, _i, C.POINTER(Column), _vp]),
     "pgsd_b200_scan_sizes": (_i, [C.POINTER(_u64), _i, _i, _i, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64)]),
     "pgsd_b200_sort_ids": (_i, [_u64, _vp, _vp, _vp, _vp]),

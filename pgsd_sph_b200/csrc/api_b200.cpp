@@ -157,6 +157,42 @@ int pgsd_b200_write_chunk_soa(struct pgsd_handle* handle, const char* name, enum
                                    (int)src_type, c, !on_device);
     }
 
+int pgsd_b200_write_chunks_soa(struct pgsd_handle* handle, int n_chunks,
+                               const struct pgsd_b200_chunk_desc* chunks)
+    {
+    if (n_chunks < 0 || (n_chunks > 0 && chunks == nullptr))
+        return PGSD_ERROR_INVALID_ARGUMENT;
+    std::vector<DeviceChunk> dc((size_t)n_chunks);
+    std::vector<Column> cols((size_t)n_chunks * 8);
+    for (int i = 0; i < n_chunks; i++)
+        {
+        const pgsd_b200_chunk_desc& d = chunks[i];
+        if (d.M == 0 || d.M > 8 || (d.N > 0 && d.cols == nullptr))
+            return PGSD_ERROR_INVALID_ARGUMENT;
+        bool on_device = true, mixed = false;
+        Column* c = &cols[(size_t)i * 8];
+        if (d.N > 0)
+            {
+            for (uint32_t j = 0; j < d.M; j++)
+                {
+                if (d.cols[j].base == nullptr)
+                    return PGSD_ERROR_INVALID_ARGUMENT;
+                c[j].base = d.cols[j].base;
+                c[j].stride = d.cols[j].stride;
+                }
+            on_device = columns_on_device(d.cols, d.M, &mixed);
+            if (mixed)
+                {
+                set_last_error("write_chunks_soa: columns must be all device or all host pointers");
+                return PGSD_ERROR_INVALID_ARGUMENT;
+                }
+            }
+        dc[(size_t)i] = DeviceChunk { d.name, (int)d.dst_type, (int)d.src_type, d.N, d.M, d.N_global, d.M_global,
+                                      d.offset, d.all, c, !on_device };
+        }
+    return file_write_chunks_device(handle, n_chunks, dc.data());
+    }
+
 int pgsd_b200_pack_soa(void* dst_device, enum pgsd_type dst_type, uint64_t N, uint32_t M,
                        enum pgsd_type src_type, const struct pgsd_b200_column* cols_device,
                        void* cuda_stream)

@@ -844,33 +844,49 @@ int flush_all(pgsd_handle* h)
     } // namespace
 
 // ------------------------------------------------------------------------------ internal API
+int file_write_chunks_device(pgsd_handle* h, int n, const DeviceChunk* chunks)
+    {
+    if (h == nullptr || h->fh == nullptr || n < 0 || (n > 0 && chunks == nullptr))
+        return PGSD_ERROR_INVALID_ARGUMENT;
+    if (h->open_flags == PGSD_OPEN_READONLY)
+        return PGSD_ERROR_FILE_MUST_BE_WRITABLE;
+    for (int i = 0; i < n; i++)
+        {
+        const DeviceChunk& c = chunks[i];
+        if (c.name == nullptr || c.M == 0 || (c.N > 0 && c.cols == nullptr))
+            return PGSD_ERROR_INVALID_ARGUMENT;
+        if (type_size(c.dst_type) == 0 || !cast_supported(c.src_type, c.dst_type))
+            return PGSD_ERROR_INVALID_ARGUMENT;
+        }
+    FileState* s = state_of(h);
+    // ONE K1 launch packs every chunk of the call into the frame arena
+    std::vector<PackRequest> reqs((size_t)n);
+    for (int i = 0; i < n; i++)
+        {
+        const DeviceChunk& c = chunks[i];
+        reqs[(size_t)i] = PackRequest { c.dst_type, c.src_type, c.N, c.M, c.cols, c.host_columns, nullptr };
+        }
+    int rc = dev_arena_pack(reqs.data(), n);
+    if (rc != 0)
+        return rc;
+    s->device_frame_open = true;
+    for (int i = 0; i < n; i++)
+        {
+        const DeviceChunk& c = chunks[i];
+        rc = record_chunk(h, c.name, c.dst_type, c.N, c.M, c.N_global, c.M_global, c.offset, c.all,
+                          ChunkSource { Src::Device, reqs[(size_t)i].arena_ptr });
+        if (rc != PGSD_SUCCESS)
+            return rc;
+        }
+    return PGSD_SUCCESS;
+    }
+
 int file_write_chunk_device(pgsd_handle* h, const char* name, int dst_type, uint64_t N, uint32_t M,
                             uint64_t N_global, uint32_t M_global, uint64_t offset, bool all, int src_type,
                             const Column* cols, bool host_columns)
     {
-    if (h == nullptr || h->fh == nullptr || name == nullptr)
-        return PGSD_ERROR_INVALID_ARGUMENT;
-    if (M == 0 || (N > 0 && cols == nullptr))
-        return PGSD_ERROR_INVALID_ARGUMENT;
-    if (h->open_flags == PGSD_OPEN_READONLY)
-        return PGSD_ERROR_FILE_MUST_BE_WRITABLE;
-    if (type_size(dst_type) == 0 || !cast_supported(src_type, dst_type))
-        return PGSD_ERROR_INVALID_ARGUMENT;
-    FileState* s = state_of(h);
-    PackRequest req;
-    req.dst_type = dst_type;
-    req.src_type = src_type;
-    req.N = N;
-    req.M = M;
-    req.cols = cols;
-    req.host_columns = host_columns;
-    req.arena_ptr = nullptr;
-    int rc = dev_arena_pack(&req, 1);
-    if (rc != 0)
-        return rc;
-    s->device_frame_open = true;
-    return record_chunk(h, name, dst_type, N, M, N_global, M_global, offset, all,
-                        ChunkSource { Src::Device, req.arena_ptr });
+    DeviceChunk c { name, dst_type, src_type, N, M, N_global, M_global, offset, all, cols, host_columns };
+    return file_write_chunks_device(h, 1, &c);
     }
 
 int file_read_to_device(pgsd_handle* h, void* dev_dst, uint64_t bytes, uint64_t file_off)
@@ -1045,24 +1061,12 @@ int pgsd_write_chunk(struct pgsd_handle* handle, const char* name, enum pgsd_typ
         return PGSD_ERROR_INVALID_ARGUMENT;
     if (N > 0 && type_size((int)type) > 0 && dev_is_device_pointer(data))
         {
-        // already packed (N, M) on the device: K1's vector-copy path moves the N*M elements into
+        // already packed (N, M) on the device: K1's vector-copy path moves the N*M elements (as one
+        // flat column; only the byte count matters to the layout) into
         // the frame arena on the caller's stream, so `data` may be reused in stream order on return
         Column one { data, 1 };
-        FileState* s = state_of(handle);
-        PackRequest req;
-        req.dst_type = (int)type;
-        req.src_type = (int)type;
-        req.N = N * M;
-        req.M = 1;
-        req.cols = &one;
-        req.host_columns = false;
-        req.arena_ptr = nullptr;
-        int rc = dev_arena_pack(&req, 1);
-        if (rc != 0)
-            return rc;
-        s->device_frame_open = true;
-        return record_chunk(handle, name, (int)type, N, M, N_global, M_global, offset, all,
-                            ChunkSource { Src::Device, req.arena_ptr });
+        DeviceChunk c { name, (int)type, (int)type, N * M, 1, N_global, M_global, offset, all, &one, false };
+        return file_write_chunks_device(handle, 1, &c);
         }
     return record_chunk(handle, name, (int)type, N, M, N_global, M_global, offset, all,
                         ChunkSource { Src::HostUser, data });

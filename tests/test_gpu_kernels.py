@@ -1,0 +1,236 @@
+"""GPU parity tests of the CUDA kernels, called through the C ABI (include/pgsd_b200.h), against the
+CPU oracles (oracle/cast_oracle.py, oracle/reorder_oracle.py).  Bit-exact: integer / byte / index
+work and IEEE casts whose result numpy defines exactly."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import cast_oracle, reorder_oracle
+from pgsd_sph_b200 import _lib
+from pgsd_sph_b200.devmem import DeviceArray
+from pgsd_sph_b200.fl import _NP_TO_PGSD
+from pgsd_sph_b200.hoomd import reorder_by_id
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cuda(lib):
+    assert lib.pgsd_b200_cuda_available() == 1, "no CUDA device: the device path has no CPU fallback"
+    _lib.check(lib.pgsd_b200_device_init(0), "device_init")
+    return lib
+
+
+def gpu_pack(lib, columns, dst_dtype):
+    """columns: list of 1-D numpy arrays (possibly strided views) of one dtype."""
+    M, N = len(columns), len(columns[0])
+    src_dt = columns[0].dtype
+    keep, cols = [], (_lib.Column * M)()
+    for j, c in enumerate(columns):
+        # upload the strided view's base buffer span, keep the stride
+        stride = c.strides[0] // src_dt.itemsize if N > 1 else 1
+        span = np.lib.stride_tricks.as_strided(c, shape=((N - 1) * stride + 1,), strides=(src_dt.itemsize,)) if N else c
+        d = DeviceArray.from_numpy(np.ascontiguousarray(span))
+        keep.append(d)
+        cols[j] = _lib.Column(d.ptr, stride)
+    out = DeviceArray((N, M), dst_dtype)
+    _lib.check(lib.pgsd_b200_pack_soa(out.ptr, _NP_TO_PGSD[np.dtype(dst_dtype)], N, M, _NP_TO_PGSD[src_dt], cols, None), "pack_soa")
+    _lib.check(lib.pgsd_b200_synchronize(), "sync")
+    return out.to_numpy()
+
+
+INT_TYPES = [np.uint8, np.uint16, np.uint32, np.uint64, np.int8, np.int16, np.int32, np.int64]
+
+
+def rand_values(rng, dt, n):
+    dt = np.dtype(dt)
+    if dt.kind == 'f':
+        a = rng.standard_normal(n) * 10.0 ** rng.integers(-30, 30, size=n)
+        return a.astype(dt)
+    info = np.iinfo(dt)
+    a = rng.integers(info.min, info.max, size=n, dtype=dt, endpoint=True)
+    return a
+
+
+@pytest.mark.parametrize("M", [1, 2, 3, 4, 7])
+@pytest.mark.parametrize("N", [0, 1, 3, 4, 5, 1000, 2049, 100003])
+def test_pack_f32_bitcopy(cuda, N, M):
+    rng = np.random.default_rng(N * 10 + M)
+    cols = [rng.standard_normal(N).astype(np.float32) for _ in range(M)]
+    got = gpu_pack(cuda, cols, np.float32)
+    assert got.tobytes() == cast_oracle.pack_soa(cols, np.float32).tobytes()
+
+
+@pytest.mark.parametrize("M", [1, 3, 4])
+@pytest.mark.parametrize("N", [1, 7, 4096, 50001])
+def test_pack_f64_to_f32_special_values(cuda, N, M):
+    rng = np.random.default_rng(N + M)
+    cols = []
+    for _ in range(M):
+        a = rand_values(rng, np.float64, N)
+        special = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1e-45, -1e-46, 3.4028235677973366e38, 3.5e38,
+                            1.0000000596046448, 1.0000001788139343, 5e-324, 1.401298464324817e-45 * 0.5])
+        k = min(N, len(special))
+        a[:k] = special[:k]
+        if N > 20:
+            # NaNs with payloads and sign
+            bits = np.array([0x7ff8000000000001, 0xfff0000000000123, 0x7ff4000012345678], dtype=np.uint64)
+            a[14:17] = bits.view(np.float64)
+        cols.append(a)
+    got = gpu_pack(cuda, cols, np.float32)
+    assert got.tobytes() == cast_oracle.pack_soa(cols, np.float32).tobytes()
+
+
+@pytest.mark.parametrize("src", INT_TYPES + [np.float32])
+@pytest.mark.parametrize("dst", INT_TYPES + [np.float32, np.float64])
+def test_pack_cast_matrix(cuda, src, dst):
+    if np.dtype(src).kind == 'f' and np.dtype(dst).kind != 'f':
+        pytest.skip("float -> integer casts are rejected (undefined out of range in numpy)")
+    rng = np.random.default_rng(np.dtype(src).num * 100 + np.dtype(dst).num)
+    N, M = 3001, 3
+    cols = [rand_values(rng, src, N) for _ in range(M)]
+    got = gpu_pack(cuda, cols, dst)
+    assert got.dtype == np.dtype(dst)
+    assert got.tobytes() == cast_oracle.pack_soa(cols, dst).tobytes()
+
+
+def test_pack_float_to_int_is_rejected(cuda):
+    d = DeviceArray.from_numpy(np.zeros(8, dtype=np.float32))
+    out = DeviceArray((8, 1), np.int32)
+    cols = (_lib.Column * 1)(_lib.Column(d.ptr, 1))
+    assert cuda.pgsd_b200_pack_soa(out.ptr, _lib.TYPE_INT32, 8, 1, _lib.TYPE_FLOAT, cols, None) == _lib.ERROR_INVALID_ARGUMENT
+
+
+@pytest.mark.parametrize("stride", [2, 4, 5])
+def test_pack_strided_columns_aos(cuda, stride):
+    """HOOMD-style AoS source (Scalar4 pos): M columns base+j with stride 4."""
+    rng = np.random.default_rng(stride)
+    N = 10007
+    aos = rng.standard_normal((N, stride)).astype(np.float32)
+    cols = [aos[:, j] for j in range(min(3, stride))]
+    got = gpu_pack(cuda, cols, np.float32)
+    assert got.tobytes() == np.ascontiguousarray(aos[:, :len(cols)]).tobytes()
+
+
+def test_pack_unaligned_falls_back_to_generic(cuda):
+    N = 5000
+    base = DeviceArray.from_numpy(np.arange(N + 1, dtype=np.float32))
+    out = DeviceArray((N, 1), np.float32)
+    cols = (_lib.Column * 1)(_lib.Column(base.ptr + 4, 1))  # 4-byte aligned only
+    _lib.check(cuda.pgsd_b200_pack_soa(out.ptr, _lib.TYPE_FLOAT, N, 1, _lib.TYPE_FLOAT, cols, None), "pack")
+    assert (out.to_numpy()[:, 0] == np.arange(1, N + 1, dtype=np.float32)).all()
+
+
+# ---------------------------------------------------------------------------- K2
+def test_scan_sizes_matches_numpy(cuda):
+    rng = np.random.default_rng(0)
+    for P, Cn in [(1, 1), (2, 10), (8, 18), (8, 5000), (3, 4097)]:
+        sizes = rng.integers(0, 2 ** 40, size=(P, Cn), dtype=np.uint64)
+        for rank in {0, P - 1, P // 2}:
+            excl = np.zeros(Cn, np.uint64)
+            total = np.zeros(Cn, np.uint64)
+            mx = np.zeros(Cn, np.uint64)
+            p64 = C.POINTER(C.c_uint64)
+            _lib.check(cuda.pgsd_b200_scan_sizes(sizes.ctypes.data_as(p64), P, Cn, rank, excl.ctypes.data_as(p64),
+                                                 total.ctypes.data_as(p64), mx.ctypes.data_as(p64)), "scan")
+            assert (excl == sizes[:rank].sum(axis=0, dtype=np.uint64)).all()
+            assert (total == sizes.sum(axis=0, dtype=np.uint64)).all()
+            assert (mx == sizes.max(axis=0)).all()
+
+
+# ---------------------------------------------------------------------------- K4 / K5
+def gpu_sort(lib, keys):
+    n = len(keys)
+    dk = DeviceArray.from_numpy(keys)
+    ds = DeviceArray((n,), np.uint32)
+    dp = DeviceArray((n,), np.uint32)
+    _lib.check(lib.pgsd_b200_sort_ids(n, dk.ptr, ds.ptr, dp.ptr, None), "sort_ids")
+    _lib.check(lib.pgsd_b200_synchronize(), "sync")
+    return ds.to_numpy(), dp.to_numpy()
+
+
+def key_cases():
+    rng = np.random.default_rng(11)
+    yield "perm_10k", rng.permutation(10000).astype(np.uint32)
+    yield "perm_1M", rng.permutation(1 << 20).astype(np.uint32)
+    yield "dups_small_range", rng.integers(0, 17, size=70001).astype(np.uint32)
+    yield "dups_byte_patterns", (rng.integers(0, 4, size=50000) * 0x01010101).astype(np.uint32)
+    yield "full_32bit", rng.integers(0, 2 ** 32, size=300007, dtype=np.uint64).astype(np.uint32)
+    yield "all_equal", np.full(12345, 77, dtype=np.uint32)
+    yield "sorted", np.arange(100000, dtype=np.uint32)
+    yield "reversed", np.arange(100000, dtype=np.uint32)[::-1].copy()
+    yield "one", np.array([5], dtype=np.uint32)
+    yield "two", np.array([9, 3], dtype=np.uint32)
+    yield "tile_edge", rng.permutation(8192 * 3 + 1).astype(np.uint32)
+    yield "high_bytes_only", (rng.integers(0, 256, size=40000) << 24).astype(np.uint32)
+    yield "max_values", np.array([0xffffffff, 0, 0xffffffff, 1, 0xfffffffe] * 1000, dtype=np.uint32)
+
+
+@pytest.mark.parametrize("name,keys", list(key_cases()), ids=[k for k, _ in key_cases()])
+def test_sort_ids_equals_stable_argsort(cuda, name, keys):
+    s, p = gpu_sort(cuda, keys)
+    o = np.argsort(keys, kind='stable')
+    assert (p == o.astype(np.uint32)).all()
+    assert (s == keys[o]).all()
+
+
+def test_sort_empty(cuda):
+    assert cuda.pgsd_b200_sort_ids(0, None, None, None, None) == 0
+
+
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 1000, 65537])
+def test_reorder_host_all_field_widths(cuda, n):
+    rng = np.random.default_rng(n)
+    ids = rng.permutation(n).astype(np.uint32)
+    fields = {
+        "position": rng.standard_normal((n, 3)).astype(np.float32),
+        "typeid": rng.integers(0, 3, size=n).astype(np.uint32),
+        "image": rng.integers(-5, 5, size=(n, 3)).astype(np.int32),
+        "mass64": rng.standard_normal(n),
+        "flags8": rng.integers(0, 255, size=n).astype(np.uint8),
+        "odd_bytes": rng.integers(0, 255, size=(n, 5)).astype(np.uint8),
+        "h16": rng.integers(0, 60000, size=(n, 3)).astype(np.uint16),
+        "wide": rng.standard_normal((n, 16)).astype(np.float32),
+    }
+    sid, out = reorder_by_id(ids, fields)
+    rsid, rout, _ = reorder_oracle.reorder(ids, fields)
+    assert (sid == rsid).all()
+    for k in fields:
+        assert out[k].tobytes() == rout[k].tobytes(), k
+
+
+def test_reorder_device_resident(cuda):
+    rng = np.random.default_rng(5)
+    n = 200003
+    ids = rng.permutation(n).astype(np.uint32)
+    pos = rng.standard_normal((n, 3)).astype(np.float32)
+    dens = rng.standard_normal(n).astype(np.float32)
+    sid, out = reorder_by_id(DeviceArray.from_numpy(ids), {"p": DeviceArray.from_numpy(pos), "d": DeviceArray.from_numpy(dens)},
+                             device=True)
+    o = np.argsort(ids, kind='stable')
+    assert (sid.to_numpy() == ids[o]).all()
+    assert out["p"].to_numpy().tobytes() == pos[o].tobytes()
+    assert out["d"].to_numpy().tobytes() == dens[o].tobytes()
+
+
+@pytest.mark.slow
+def test_reorder_16M_size_independent_properties(cuda):
+    """BASELINE config-4 size (16 Mi particles): dense unique ids -> sorted ids are 0..N-1, the
+    permutation is a bijection, and a payload that encodes its own id lands at row id."""
+    n = 1 << 24
+    rng = np.random.default_rng(2026)
+    ids = rng.permutation(n).astype(np.uint32)
+    payload = np.empty((n, 3), dtype=np.float32)
+    payload[:, 0] = ids
+    payload[:, 1] = ids * np.float32(0.5)
+    payload[:, 2] = -ids.astype(np.float32)
+    tag = (ids ^ np.uint32(0x9e3779b9)).astype(np.uint32)
+    sid, out = reorder_by_id(ids, {"payload": payload, "tag": tag})
+    ar = np.arange(n, dtype=np.uint32)
+    assert (sid == ar).all()
+    assert (out["tag"] == (ar ^ np.uint32(0x9e3779b9))).all()
+    assert (out["payload"][:, 0] == ar.astype(np.float32)).all()
+    assert (out["payload"][:, 2] == -ar.astype(np.float32)).all()
+    # checksum of checksums: a permutation preserves the multiset
+    assert int(out["tag"].astype(np.uint64).sum()) == int(tag.astype(np.uint64).sum())
