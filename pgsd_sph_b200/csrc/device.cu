@@ -230,6 +230,8 @@ void stager_main()
         }
     }
 
+void stop_threads_at_exit();
+
 int start_threads()
     {
     if (g.threads_running)
@@ -242,12 +244,23 @@ int start_threads()
         g.free_slots.push_back((int)i);
         }
     g.stop = false;
+    static bool exit_hook = false;
+    if (!exit_hook)
+        {
+        // joinable std::thread objects must not reach static destruction: finish queued file
+        // writes and join at exit (registered after the CUDA runtime came up, so it runs first)
+        atexit([]() { dev_drain(); stop_threads_at_exit(); });
+        exit_hook = true;
+        }
     g.stager = std::thread(stager_main);
     for (uint32_t i = 0; i < g.n_writers; i++)
         g.writers.emplace_back(writer_main);
     g.threads_running = true;
     return 0;
     }
+
+void stop_threads();
+void stop_threads_at_exit() { stop_threads(); }
 
 void stop_threads()
     {

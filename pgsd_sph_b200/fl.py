@@ -283,6 +283,66 @@ class PGSDFile:
         del keep
         _raise_on_error(retval, self._name)
 
+    def _soa_views(self, name, columns):
+        """-> (M x (ptr, stride), N, src dtype, keep-alive list) for 1..8 equally long 1-D columns."""
+        M = len(columns)
+        if M < 1 or M > 8:
+            raise ValueError("write_chunk_soa takes 1..8 columns: " + name)
+        views, keep = [], []
+        for c in columns:
+            if is_device_array(c):
+                ptr, shape, cdt, strides, k = as_device_view(c)
+                keep.append(k)
+                on_device = True
+            else:
+                a = numpy.asarray(c)
+                ptr, shape, cdt, strides = a.ctypes.data, a.shape, a.dtype, a.strides
+                keep.append(a)
+                on_device = False
+            if len(shape) != 1:
+                raise ValueError("write_chunk_soa columns must be 1-dimensional: " + name)
+            st = cdt.itemsize if strides is None else strides[0]
+            if st % cdt.itemsize:
+                raise ValueError("column stride is not a multiple of the item size: " + name)
+            views.append((ptr, int(shape[0]), cdt, st // cdt.itemsize, on_device))
+        N, src_dt = views[0][1], views[0][2]
+        if any(v[1] != N or v[2] != src_dt or v[4] != views[0][4] for v in views):
+            raise ValueError("write_chunk_soa columns must share length, dtype and memory space: " + name)
+        return views, N, src_dt, keep
+
+    def prepare_frame_soa(self, chunks, rank=0):
+        """Build the reusable C descriptor table for :py:meth:`write_frame_soa`.
+
+        ``chunks``: sequence of ``(name, columns, dtype, offset, write_all)`` with the meaning of
+        :py:meth:`write_chunk_soa`'s arguments.  The returned object keeps the arrays alive and can
+        be written any number of times (one simulation's buffers, one frame per time step).
+        """
+        n = len(chunks)
+        descs = (_lib.ChunkDesc * max(n, 1))()
+        keep = []
+        for i, (name, columns, dtype, offset, write_all) in enumerate(chunks):
+            views, N, src_dt, k = self._soa_views(name, columns)
+            M = len(views)
+            src_type = _NP_TO_PGSD.get(src_dt)
+            dst_type = _NP_TO_PGSD.get(numpy.dtype(dtype) if dtype is not None else src_dt)
+            if src_type is None or dst_type is None:
+                raise ValueError("invalid type for chunk: " + name)
+            N_global, stride = self._offset_args(N, M, offset, rank)
+            cols = (_lib.Column * M)(*[_lib.Column(v[0] if N else None, v[3]) for v in views])
+            bname = name.encode('utf-8')
+            keep.extend([k, cols, bname])
+            descs[i] = _lib.ChunkDesc(bname, dst_type, src_type, N, M, N_global, M, stride, bool(write_all),
+                                      cols)
+        return (descs, n, keep)
+
+    def write_frame_soa(self, prepared):
+        """Write all SoA chunks of a frame with ONE K1 launch (``pgsd_b200_write_chunks_soa``);
+        ``prepared`` comes from :py:meth:`prepare_frame_soa`.  Equivalent to calling
+        :py:meth:`write_chunk_soa` for each chunk in order."""
+        self._check_open()
+        descs, n, _ = prepared
+        _raise_on_error(self._lib.pgsd_b200_write_chunks_soa(C.byref(self._handle), n, descs), self._name)
+
     # ------------------------------------------------------------------ read
     def chunk_exists(self, frame, name, write_all=True):
         """Test if a chunk exists (ref: fl.pyx:656-715)."""
