@@ -41,7 +41,9 @@ int main(int argc, char** argv)
         if (posix_fallocate(fd, 0, (off_t)total) != 0)
             perror("fallocate");
         }
-    if (mode == "mmap")
+    const bool populate = (mode == "mmap_pop");
+    const bool piecewise = (mode == "mmap_piece" || mode == "mmap_piece_pop");
+    if (mode == "mmap" || mode == "mmap_pop")
         {
         if (ftruncate(fd, (off_t)total) != 0)
             perror("ftruncate");
@@ -57,8 +59,23 @@ int main(int argc, char** argv)
                 if (off >= total)
                     return;
                 size_t len = total - off < piece ? total - off : piece;
-                if (map)
+                if (piecewise)
+                    {
+                    // what a writer thread of the library would do: extend, map the piece, copy, unmap
+                    if (fallocate(fd, 0, (off_t)(off + len - 1), 1) != 0)
+                        perror("fallocate");
+                    char* m = (char*)mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_SHARED, fd, (off_t)off);
+                    if (mode == "mmap_piece_pop")
+                        madvise(m, len, 23 /* MADV_POPULATE_WRITE */);
+                    memcpy(m, src[(size_t)t], len);
+                    munmap(m, len);
+                    }
+                else if (map)
+                    {
+                    if (populate)
+                        madvise(map + off, len, 23 /* MADV_POPULATE_WRITE */);
                     memcpy(map + off, src[(size_t)t], len);
+                    }
                 else
                     {
                     size_t done = 0;
