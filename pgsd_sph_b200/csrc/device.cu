@@ -1015,24 +1015,7 @@ Comm* make_nccl_comm(int rank, int nprocs, const void* unique_id, int device, st
 int dev_reorder(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, uint32_t* perm, int nfields,
                 const ReorderField* fields, void* stream)
     {
-    int rc = dev_init(-1);
-    if (rc != 0)
-        return rc;
-    if (n == 0)
-        return 0;
-    uint32_t* p = perm;
-    if (p == nullptr)
-        {
-        // the permutation is needed even when the caller does not want it back
-        rc = scratch_reserve((size_t)n * 4);
-        if (rc != 0)
-            return rc;
-        p = (uint32_t*)g.scratch;
-        }
-    rc = dev_sort_ids(n, keys, keys_sorted, p, stream);
-    if (rc != 0)
-        return rc;
-    return dev_gather(n, p, nfields, fields, stream);
+    return dev_reorder_rows(n, keys, keys_sorted, perm, nfields, fields, stream);
     }
 
 // ------------------------------------------------------------------------------ reorder, host buffers
@@ -1079,10 +1062,7 @@ int dev_reorder_host(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, ui
         CUDA_TRY(cudaMemcpyAsync((void*)df[i].in, fields[i].in, b, cudaMemcpyHostToDevice, st), -1);
         g_stats.h2d_bytes += b;
         }
-    rc = dev_sort_ids(n, d_keys, d_sorted, d_perm, st);
-    if (rc != 0)
-        return rc;
-    rc = dev_gather(n, d_perm, nfields, df.data(), st);
+    rc = dev_reorder_rows(n, d_keys, d_sorted, perm ? d_perm : nullptr, nfields, df.data(), st);
     if (rc != 0)
         return rc;
     if (keys_sorted)

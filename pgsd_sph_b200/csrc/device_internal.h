@@ -12,6 +12,8 @@ namespace pgsdb
 {
 int dev_sm_count();               // valid after dev_init()
 void sort_release_workspace();    // kernels_sort.cu
+int dev_reorder_rows(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, uint32_t* perm, int nfields,
+                     const ReorderField* fields, void* stream); // kernels_sort.cu
 
 // pgsd_type codes (include/pgsd.h; ref: /root/reference/pgsd/pgsd/pgsd.h:38-69)
 enum : int

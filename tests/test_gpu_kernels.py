@@ -234,3 +234,76 @@ def test_reorder_16M_size_independent_properties(cuda):
     assert (out["payload"][:, 2] == -ar.astype(np.float32)).all()
     # checksum of checksums: a permutation preserves the multiset
     assert int(out["tag"].astype(np.uint64).sum()) == int(tag.astype(np.uint64).sum())
+
+
+# ---- bucket pass (rows grouped by the top key bits before the pair passes) and both rank modes
+def _reorder_device_full(lib, keys, fields, want_perm=True):
+    n = len(keys)
+    dk = DeviceArray.from_numpy(keys)
+    ds, dp = DeviceArray((n,), np.uint32), DeviceArray((n,), np.uint32)
+    din = [DeviceArray.from_numpy(f) for f in fields]
+    dout = [DeviceArray(f.shape, f.dtype) for f in fields]
+    fl_ = (_lib.Field * max(len(fields), 1))(*[
+        _lib.Field(i.ptr, o.ptr, f.dtype.itemsize * (int(np.prod(f.shape[1:])) if f.ndim > 1 else 1))
+        for i, o, f in zip(din, dout, fields)])
+    _lib.check(lib.pgsd_b200_reorder_device(n, dk.ptr, ds.ptr, dp.ptr if want_perm else None, len(fields), fl_, None),
+               "reorder_device")
+    _lib.check(lib.pgsd_b200_synchronize(), "sync")
+    return ds.to_numpy(), (dp.to_numpy() if want_perm else None), [o.to_numpy() for o in dout]
+
+
+def bucket_key_cases():
+    rng = np.random.default_rng(23)
+    yield "perm_70k", rng.permutation(70001).astype(np.uint32)                       # 17 bits: 3 byte passes
+    yield "perm_300k", rng.permutation(300000).astype(np.uint32)
+    yield "dups_2bytes", rng.integers(0, 40000, size=123457).astype(np.uint32)       # duplicates: stability
+    yield "one_byte_direct", rng.integers(0, 200, size=50001).astype(np.uint32)      # npass == 1: bucket pass is the sort
+    yield "high_byte_direct", (rng.integers(0, 256, size=40000) << 24).astype(np.uint32)
+    yield "full_32bit", rng.integers(0, 2 ** 32, size=200003, dtype=np.uint64).astype(np.uint32)
+    yield "const_high_bits", (rng.integers(0, 3000, size=99999) + 0xABC00000).astype(np.uint32)
+    yield "all_equal", np.full(5000, 9, dtype=np.uint32)
+    yield "tile_edges", rng.permutation(4096 * 5).astype(np.uint32)
+    yield "skewed", np.minimum(rng.geometric(0.001, size=150000), 2 ** 20).astype(np.uint32)
+
+
+@pytest.mark.parametrize("rank_mode", ["ballot", "match"])
+@pytest.mark.parametrize("name,keys", list(bucket_key_cases()), ids=[k for k, _ in bucket_key_cases()])
+def test_reorder_bucket_path_equals_stable_argsort(cuda, monkeypatch, name, keys, rank_mode):
+    monkeypatch.setenv("PGSD_B200_BUCKET_MIN_ROWS", "0")
+    monkeypatch.setenv("PGSD_B200_RANK_MODE", rank_mode)
+    n = len(keys)
+    rng = np.random.default_rng(n)
+    fields = [rng.standard_normal((n, 3)).astype(np.float32), rng.integers(0, 2 ** 32, size=n, dtype=np.uint64).astype(np.uint32),
+              rng.standard_normal((n, 4)).astype(np.float32), rng.standard_normal(n), np.arange(n, dtype=np.uint32)]
+    o = np.argsort(keys, kind='stable')
+    for want_perm in (True, False):
+        s, p, outs = _reorder_device_full(cuda, keys, fields, want_perm)
+        assert (s == keys[o]).all()
+        if want_perm:
+            assert (p == o.astype(np.uint32)).all()
+        for f, g in zip(fields, outs):
+            assert g.tobytes() == f[o].tobytes()
+
+
+def test_reorder_bucket_path_wide_rows(cuda, monkeypatch):
+    """Rows wider than the staging buffer share (16 words) take several staging rounds."""
+    monkeypatch.setenv("PGSD_B200_BUCKET_MIN_ROWS", "0")
+    rng = np.random.default_rng(3)
+    n = 30011
+    keys = rng.permutation(n).astype(np.uint32)
+    fields = [rng.standard_normal((n, 16)).astype(np.float32), rng.standard_normal((n, 5)).astype(np.float32)]
+    o = np.argsort(keys, kind='stable')
+    s, p, outs = _reorder_device_full(cuda, keys, fields)
+    assert (s == keys[o]).all() and (p == o.astype(np.uint32)).all()
+    for f, g in zip(fields, outs):
+        assert g.tobytes() == f[o].tobytes()
+
+
+@pytest.mark.parametrize("rank_mode", ["ballot", "match"])
+def test_sort_ids_rank_modes(cuda, monkeypatch, rank_mode):
+    monkeypatch.setenv("PGSD_B200_RANK_MODE", rank_mode)
+    rng = np.random.default_rng(8)
+    keys = rng.integers(0, 2 ** 20, size=250001).astype(np.uint32)
+    s, p = gpu_sort(cuda, keys)
+    o = np.argsort(keys, kind='stable')
+    assert (p == o.astype(np.uint32)).all() and (s == keys[o]).all()
