@@ -261,16 +261,17 @@ def run_read_leg(lib, dist, args, peaks, windows):
     for _ in range(args.warmup):
         step_dev()
     lib.pgsd_b200_synchronize()
-    # per-kernel-group times (sort = census + 4 kernels per pass; gather = 1 launch)
+    # per-phase device times of the real path (CUDA events recorded by the library on the stream)
     tm = Timer(lib)
-    sort_ms, gather_ms = [], []
+    lib.pgsd_b200_reorder_profiling(1)
+    phases = []
     for _ in range(3):
-        tm.start()
-        _lib.check(lib.pgsd_b200_sort_ids(n, d_ids.ptr, d_sorted.ptr, d_perm.ptr, None), "sort")
-        sort_ms.append(tm.stop())
-        tm.start()
-        _lib.check(lib.pgsd_b200_gather(n, d_perm.ptr, 5, fields, None), "gather")
-        gather_ms.append(tm.stop())
+        step_dev()
+        ms = (C.c_float * 4)()
+        lib.pgsd_b200_reorder_phase_ms(ms)
+        phases.append([float(x) for x in ms])
+    lib.pgsd_b200_reorder_profiling(0)
+    phase_ms = [min(p[i] for p in phases) for i in range(4)]
     lib.pgsd_b200_reset_stats()
     dist.barrier()
     lib.pgsd_b200_synchronize()
@@ -326,14 +327,16 @@ def run_read_leg(lib, dist, args, peaks, windows):
     os.unlink(path)
 
     peak = peaks["hbm_gbs"]
-    sort_s, gather_s = min(sort_ms) * 1e-3, min(gather_ms) * 1e-3
+    def kern(ms, bytes_pp, note):
+        t = max(ms, 1e-6) * 1e-3
+        return {"ms": ms, "algorithmic_bytes": bytes_pp * n, "GBps": bytes_pp * n / t / 1e9,
+                "frac": bytes_pp * n / t / 1e9 / peak, "note": note}
+
     kernels = {
-        "k4_sort_ids": {"ms": sort_s * 1e3, "algorithmic_bytes": 68 * n, "GBps": 68 * n / sort_s / 1e9,
-                        "frac": 68 * n / sort_s / 1e9 / peak,
-                        "note": "census 4 B + 4 LSD passes x 16 B (key,idx) per particle"},
-        "k5_gather": {"ms": gather_s * 1e3, "algorithmic_bytes": 76 * n, "GBps": 76 * n / gather_s / 1e9,
-                      "frac": 76 * n / gather_s / 1e9 / peak,
-                      "note": "perm 4 B + 36 B payload read + 36 B written per particle"},
+        "k4_digit_census": kern(phase_ms[0], 4, "keys read once; includes the 8 KB D2H + host sync"),
+        "k4_bucket_rows": kern(phase_ms[1], 4 + 2 * 40, "tile histogram (4 B) + rows moved once: 40 B read + 40 B written"),
+        "k4_pair_passes": kern(phase_ms[2], 3 * 4 + (4 + 8) + 2 * 16, "3 LSD passes: histogram 4 B each; (key,idx) 12/16/16 B"),
+        "k5_gather": kern(phase_ms[3], 4 + 2 * 36, "perm 4 B + 36 B payload read + 36 B written"),
     }
     reorder_s = dev_ms * 1e-3 / args.steps
     return {

@@ -187,6 +187,11 @@ int pgsd_b200_timer_start(void* t);
 int pgsd_b200_timer_stop(void* t, float* ms);
 int pgsd_b200_timer_destroy(void* t);
 int pgsd_b200_flush_l2(void);
+/* Per-phase device time of the last pgsd_b200_reorder_device call that took the bucketed path
+   (CUDA events on the caller's stream): out4 = {key census, bucket pass, pair passes, gather} in ms.
+   Measurement hook for bench.py; off by default. */
+int pgsd_b200_reorder_profiling(int on);
+int pgsd_b200_reorder_phase_ms(float* out4);
 
 #ifdef __cplusplus
 }

@@ -97,6 +97,10 @@ int dev_reorder(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, uint32_
 int dev_reorder_host(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, uint32_t* perm,
                      int nfields, const ReorderField* fields);
 
+// phase timing of the last bucketed reorder (CUDA events): census, bucket pass, pair passes, gather
+void dev_reorder_profiling(bool on);
+int dev_reorder_phase_ms(float* out4);
+
 // ---- plain device / pinned memory helpers for callers without a CUDA runtime of their own
 int dev_malloc(void** p, uint64_t bytes);
 int dev_free(void* p);

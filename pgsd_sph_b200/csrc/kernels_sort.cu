@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k4_tile_histogram(const uint32_t
     __syncthreads();
     const uint64_t base = (uint64_t)blockIdx.x * SORT_TILE;
     unsigned int* mine = h[(threadIdx.x >> 5) & (SORT_WARPS / 4 - 1)];
-    if (base + SORT_TILE <= n)
+    if (ITEMS >= 4 && base + SORT_TILE <= n)
         {
         const uint4* k4 = reinterpret_cast<const uint4*>(keys + base);
 #pragma unroll
@@ -140,7 +140,8 @@ __global__ void __launch_bounds__(SORT_THREADS) k4_tile_histogram(const uint32_t
         }
     else
         {
-        for (uint64_t i = base + threadIdx.x; i < n; i += SORT_THREADS)
+        const uint64_t end = base + SORT_TILE < n ? base + SORT_TILE : n;
+        for (uint64_t i = base + threadIdx.x; i < end; i += SORT_THREADS)
             atomicAdd(&mine[(keys[i] >> shift) & 255u], 1u);
         }
     __syncthreads();
@@ -246,44 +247,48 @@ __device__ __forceinline__ void tile_rank(const uint32_t (&key)[ITEMS], uint32_t
     __syncthreads();
     uint32_t* myhist = sm.whist + w * RADIX;
     const unsigned lt = lanemask_lt();
+    // (a) peers of every item: register-only work, all ballots of the tile pipeline freely
+    unsigned peers[ITEMS];
 #pragma unroll
     for (int k = 0; k < ITEMS; k++)
         {
         const uint32_t e = wbase + k * 32 + lane;
         const bool valid = e < tile_n;
         const uint32_t d = (key[k] >> shift) & 255u;
-        unsigned peers;
         if (RM == RANK_MATCH)
             {
             // invalid lanes (tile tail) match among themselves on an out-of-range value
-            peers = __match_any_sync(0xffffffffu, valid ? d : 0x100u);
+            peers[k] = __match_any_sync(0xffffffffu, valid ? d : 0x100u);
             }
         else
             {
-            peers = __ballot_sync(0xffffffffu, valid);
+            unsigned m = __ballot_sync(0xffffffffu, valid);
 #pragma unroll
             for (int bit = 0; bit < 8; bit++)
                 {
                 const bool one = (d >> bit) & 1u;
                 const unsigned bal = __ballot_sync(0xffffffffu, one);
-                peers &= one ? bal : ~bal;
+                m &= one ? bal : ~bal;
                 }
+            peers[k] = m;
             }
-        uint32_t r = 0;
+        }
+    // (b) running per-warp digit counts: every peer reads the count (one broadcast read), then the
+    //     group's first lane adds the group size -- a short read -> write chain per item
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++)
+        {
+        const uint32_t e = wbase + k * 32 + lane;
+        const bool valid = e < tile_n;
+        const uint32_t d = (key[k] >> shift) & 255u;
+        uint32_t old = 0;
         if (valid)
-            {
-            const int leader = __ffs(peers) - 1;
-            uint32_t old = 0;
-            if (lane == leader)
-                {
-                old = myhist[d];
-                myhist[d] = old + __popc(peers);
-                }
-            old = __shfl_sync(peers, old, leader);
-            r = old + __popc(peers & lt);
-            }
-        pos[k] = r;
+            old = myhist[d];
         __syncwarp();
+        if (valid && (peers[k] & lt) == 0)
+            myhist[d] = old + __popc(peers[k]);
+        __syncwarp();
+        pos[k] = old + __popc(peers[k] & lt);
         }
     __syncthreads();
 
@@ -607,6 +612,278 @@ __global__ void __launch_bounds__(SORT_THREADS)
 constexpr size_t ROWS_SMEM = (size_t)(ROWS_TILE + ROWS_STAGE_WORDS + SORT_WARPS * RADIX + RADIX) * sizeof(uint32_t)
                              + ROWS_TILE * sizeof(uint16_t) + RADIX * sizeof(unsigned long long);
 
+// ---- bucket pass, AoS flavour (the fast path) ----------------------------------------------------
+// Same stable partition, but the bucketed copy is ONE array of interleaved rows (all fields of a
+// particle side by side, RW words).  The whole tile is staged in shared memory in sorted order and
+// leaves as one contiguous run per bucket (hundreds of bytes instead of one short run per field);
+// the gather that follows reads 2 sectors per particle instead of one per field.
+struct AosField
+    {
+    const uint32_t* in; // n rows of `words` words; NULL: the row's original index
+    uint32_t* out;      // final destination (used by k5_gather_aos only)
+    uint32_t words;
+    uint32_t off;       // word offset inside the interleaved row
+    };
+struct AosArgs
+    {
+    AosField f[MAX_ROW_FIELDS];
+    int nfields;
+    uint32_t row_words; // RW
+    };
+
+template <int ITEMS, int RM>
+__global__ void __launch_bounds__(SORT_THREADS)
+    k4_bucket_aos(const uint32_t* __restrict__ keys_in, uint32_t* __restrict__ keys_out, uint32_t* __restrict__ aos_out,
+                  uint64_t n, int shift, uint32_t ntiles, const uint32_t* __restrict__ tile_offset,
+                  const unsigned long long* __restrict__ digit_base, const __grid_constant__ AosArgs args)
+    {
+    constexpr int TILE = SORT_THREADS * ITEMS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t* skeys = reinterpret_cast<uint32_t*>(smem_raw);          // TILE : keys in tile-sorted order
+    uint16_t* spos = reinterpret_cast<uint16_t*>(skeys + TILE);       // TILE : row -> sorted position
+    TileRankSmem sm;
+    sm.whist = reinterpret_cast<uint32_t*>(spos + TILE);
+    sm.dstart = sm.whist + SORT_WARPS * RADIX;
+    sm.gdelta = reinterpret_cast<unsigned long long*>(sm.dstart + RADIX);
+    uint32_t* stage = reinterpret_cast<uint32_t*>(sm.gdelta + RADIX); // TILE * RW
+    __shared__ uint32_t wtot[8];
+    sm.wtot = wtot;
+
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const uint32_t RW = args.row_words;
+    const uint64_t tile_base = (uint64_t)blockIdx.x * TILE;
+    const uint32_t tile_n = (uint32_t)((n - tile_base) < (uint64_t)TILE ? (n - tile_base) : TILE);
+    const uint32_t wbase = (uint32_t)w * (32 * ITEMS);
+
+    uint32_t key[ITEMS], pos[ITEMS];
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++)
+        {
+        const uint32_t e = wbase + k * 32 + lane;
+        key[k] = e < tile_n ? ld_stream_u32(keys_in + tile_base + e) : 0xffffffffu;
+        }
+    tile_rank<ITEMS, RM>(key, pos, tile_n, shift, sm, ntiles, tile_offset, digit_base);
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++)
+        {
+        const uint32_t e = wbase + k * 32 + lane;
+        if (e < tile_n)
+            {
+            skeys[pos[k]] = key[k];
+            spos[e] = (uint16_t)pos[k];
+            }
+        }
+    __syncthreads();
+    // fields -> interleaved rows in shared memory, in sorted order.  Global loads are flat and
+    // coalesced (16-byte vectors on full, aligned tiles) and issued in batches before their stores.
+    for (int fi = 0; fi < args.nfields; fi++)
+        {
+        const AosField f = args.f[fi];
+        const uint32_t W = f.words;
+        if (f.in == nullptr)
+            {
+            for (uint32_t e = tid; e < tile_n; e += SORT_THREADS)
+                stage[(uint32_t)spos[e] * RW + f.off] = (uint32_t)(tile_base + e);
+            continue;
+            }
+        const uint32_t total = tile_n * W;
+        const uint32_t* in = f.in + tile_base * W;
+        if (tile_n == TILE && (reinterpret_cast<uintptr_t>(in) & 15u) == 0)
+            {
+            const uint4* in4 = reinterpret_cast<const uint4*>(in);
+            const uint32_t nvec = total / 4; // TILE * W / 4, a multiple of SORT_THREADS * ITEMS / 4
+            for (uint32_t v0 = 0; v0 < nvec; v0 += 4 * SORT_THREADS)
+                {
+                uint4 v[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    {
+                    const uint32_t vq = v0 + tid + k * SORT_THREADS;
+                    if (vq < nvec)
+                        v[k] = ldg_stream_v4(in4 + vq);
+                    }
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    {
+                    const uint32_t vq = v0 + tid + k * SORT_THREADS;
+                    if (vq < nvec)
+                        {
+                        const uint32_t words[4] = { v[k].x, v[k].y, v[k].z, v[k].w };
+                        uint32_t e = (vq * 4) / W, c = vq * 4 - e * W;
+#pragma unroll
+                        for (int u = 0; u < 4; u++)
+                            {
+                            stage[(uint32_t)spos[e] * RW + f.off + c] = words[u];
+                            if (++c == W)
+                                {
+                                c = 0;
+                                e++;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        else
+            {
+            for (uint32_t q0 = 0; q0 < total; q0 += 8 * SORT_THREADS)
+                {
+                uint32_t v[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    {
+                    const uint32_t q = q0 + tid + k * SORT_THREADS;
+                    v[k] = q < total ? ld_stream_u32(in + q) : 0u;
+                    }
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    {
+                    const uint32_t q = q0 + tid + k * SORT_THREADS;
+                    if (q < total)
+                        {
+                        const uint32_t e = q / W, c = q - e * W;
+                        stage[(uint32_t)spos[e] * RW + f.off + c] = v[k];
+                        }
+                    }
+                }
+            }
+        }
+    __syncthreads();
+    // out: keys as digit runs; rows as one contiguous run of RW-word records per digit
+    if (keys_out)
+        {
+#pragma unroll
+        for (int k = 0; k < ITEMS; k++)
+            {
+            const uint32_t j = tid + k * SORT_THREADS;
+            if (j < tile_n)
+                {
+                const uint32_t kv = skeys[j];
+                keys_out[sm.gdelta[(kv >> shift) & 255u] + j] = kv;
+                }
+            }
+        }
+    const uint32_t total_out = tile_n * RW;
+    uint32_t j = tid / RW, c = tid - j * RW;
+    const uint32_t dj = SORT_THREADS / RW, dc = SORT_THREADS - dj * RW;
+    for (uint32_t q = tid; q < total_out; q += SORT_THREADS)
+        {
+        const unsigned long long g = sm.gdelta[(skeys[j] >> shift) & 255u] + j;
+        aos_out[g * RW + c] = stage[q];
+        j += dj;
+        c += dc;
+        if (c >= RW)
+            {
+            c -= RW;
+            j++;
+            }
+        }
+    }
+
+template <int ITEMS> constexpr size_t aos_smem_fixed()
+    {
+    return (size_t)SORT_THREADS * ITEMS * (sizeof(uint32_t) + sizeof(uint16_t))
+           + (size_t)(SORT_WARPS * RADIX + RADIX) * sizeof(uint32_t) + RADIX * sizeof(unsigned long long);
+    }
+
+// ---- K5, AoS flavour: out_f[i] = row perm[i] of the bucketed copy, split back into the fields -----
+// A warp owns 4 chunks of 32 consecutive output rows.  The source rows go global -> shared with
+// cp.async (no registers held while ~40 random 4/8-byte reads per lane are in flight), then every
+// field is written out fully coalesced from the staged rows.
+constexpr int AOS_MAX_ROW_WORDS = 40;
+constexpr int GA_THREADS = 128;
+constexpr int GA_CHUNKS = 4;
+constexpr int GA_ROWS_PER_CTA = (GA_THREADS / 32) * 32 * GA_CHUNKS;
+
+template <int VEC> // words per cp.async: 2 when RW is even and the copy is 8-byte aligned, else 1
+__global__ void __launch_bounds__(GA_THREADS)
+    k5_gather_aos(const uint32_t* __restrict__ perm, uint64_t n, const uint32_t* __restrict__ aos,
+                  const __grid_constant__ AosArgs args)
+    {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t RW = args.row_words;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t* stage = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)w * (GA_CHUNKS * 32) * RW;
+    const uint64_t warp_row0 = (uint64_t)blockIdx.x * GA_ROWS_PER_CTA + (uint64_t)w * (32 * GA_CHUNKS);
+    if (warp_row0 >= n)
+        return;
+    uint32_t p[GA_CHUNKS], rows[GA_CHUNKS];
+#pragma unroll
+    for (int g = 0; g < GA_CHUNKS; g++)
+        {
+        const uint64_t row0 = warp_row0 + 32 * g;
+        rows[g] = row0 >= n ? 0u : (uint32_t)((n - row0) < 32 ? (n - row0) : 32);
+        p[g] = lane < rows[g] ? ld_stream_u32(perm + row0 + lane) : 0u;
+        }
+    const uint32_t RV = RW / VEC; // copies per row
+#pragma unroll
+    for (int g = 0; g < GA_CHUNKS; g++)
+        {
+        const uint32_t total = rows[g] * RV;
+        uint32_t r = lane / RV, c = lane - r * RV;
+        const uint32_t dr = 32 / RV, dc = 32 - dr * RV;
+        for (uint32_t q = lane; q < 32 * RV; q += 32)
+            {
+            const uint32_t src = __shfl_sync(0xffffffffu, p[g], r & 31);
+            if (q < total)
+                {
+                const uint32_t* gp = aos + (uint64_t)src * RW + c * VEC;
+                const uint32_t sp = (uint32_t)__cvta_generic_to_shared(stage + (size_t)g * 32 * RW + q * VEC);
+                if (VEC == 2)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sp), "l"(gp) : "memory");
+                else
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sp), "l"(gp) : "memory");
+                }
+            r += dr;
+            c += dc;
+            if (c >= RV)
+                {
+                c -= RV;
+                r++;
+                }
+            }
+        }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    for (int fi = 0; fi < args.nfields; fi++)
+        {
+        const AosField f = args.f[fi];
+        const uint32_t W = f.words;
+#pragma unroll
+        for (int g = 0; g < GA_CHUNKS; g++)
+            {
+            const uint32_t* srow = stage + (size_t)g * 32 * RW + f.off;
+            uint32_t* out = f.out + (warp_row0 + 32 * g) * W;
+            const uint32_t total = rows[g] * W;
+            if (W == 1)
+                {
+                if (lane < total)
+                    out[lane] = srow[lane * RW];
+                }
+            else if (W == 3)
+                {
+#pragma unroll
+                for (int i = 0; i < 3; i++)
+                    {
+                    const uint32_t q = i * 32 + lane;
+                    const uint32_t r = q / 3, c = q - r * 3;
+                    if (q < total)
+                        out[q] = srow[r * RW + c];
+                    }
+                }
+            else
+                {
+                for (uint32_t q = lane; q < total; q += 32)
+                    {
+                    const uint32_t r = q / W, c = q - r * W;
+                    out[q] = srow[r * RW + c];
+                    }
+                }
+            }
+        }
+    }
+
 __global__ void k4_iota(uint32_t* __restrict__ perm, uint64_t n)
     {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -783,6 +1060,38 @@ void sort_release_workspace()
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// optional phase timing of the last reorder (CUDA events on the caller's stream)
+static bool g_phase_prof = false;
+static cudaEvent_t g_phase_ev[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
+static int g_phase_n = 0;
+static void phase_mark(int i, cudaStream_t st)
+    {
+    if (!g_phase_prof)
+        return;
+    if (!g_phase_ev[i])
+        cudaEventCreate(&g_phase_ev[i]);
+    cudaEventRecord(g_phase_ev[i], st);
+    g_phase_n = i + 1;
+    }
+void dev_reorder_profiling(bool on)
+    {
+    g_phase_prof = on;
+    g_phase_n = 0;
+    }
+// out[0..3] = census, bucket pass, pair passes, gather (ms); phases that did not run are 0
+int dev_reorder_phase_ms(float* out)
+    {
+    for (int i = 0; i < 4; i++)
+        out[i] = 0.f;
+    if (g_phase_n < 2)
+        return -2;
+    if (cudaEventSynchronize(g_phase_ev[g_phase_n - 1]) != cudaSuccess)
+        return -1;
+    for (int i = 0; i + 1 < g_phase_n; i++)
+        cudaEventElapsedTime(&out[i], g_phase_ev[i], g_phase_ev[i + 1]);
+    return 0;
+    }
+
 static int rank_mode()
     {
     // read on every call (cheap) so that tests can switch it
@@ -801,6 +1110,15 @@ static int sort_setup()
         cudaFuncSetAttribute(k4_scatter<false, RANK_MATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCATTER_SMEM);
         cudaFuncSetAttribute(k4_bucket_rows<RANK_BALLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ROWS_SMEM);
         cudaFuncSetAttribute(k4_bucket_rows<RANK_MATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ROWS_SMEM);
+        const int big = 200 * 1024;
+        cudaFuncSetAttribute(k4_bucket_aos<4, RANK_BALLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(k4_bucket_aos<2, RANK_BALLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(k4_bucket_aos<1, RANK_BALLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(k4_bucket_aos<4, RANK_MATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(k4_bucket_aos<2, RANK_MATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(k4_bucket_aos<1, RANK_MATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(k5_gather_aos<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(k5_gather_aos<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
         attr_done = true;
         }
     if (!g_census_host && cudaHostAlloc((void**)&g_census_host, 4 * RADIX * 8, cudaHostAllocDefault) != cudaSuccess)
@@ -812,7 +1130,8 @@ static int sort_setup()
     return 0;
     }
 
-// pass tables shared by the pair passes and the bucket pass (tile count of the finer tiling)
+// pass tables shared by the pair passes and the bucket pass (sized for the finest tiling)
+constexpr int MIN_TILE = SORT_THREADS;
 struct PassTables
     {
     uint32_t* counts;
@@ -822,12 +1141,12 @@ struct PassTables
     };
 static size_t pass_tables_bytes(uint64_t n)
     {
-    const size_t ntiles = (size_t)((n + ROWS_TILE - 1) / ROWS_TILE);
+    const size_t ntiles = (size_t)((n + MIN_TILE - 1) / MIN_TILE);
     return align_up((size_t)RADIX * ntiles * 4, 256) + 2 * RADIX * 8 + 4 * RADIX * 8;
     }
 static PassTables pass_tables_at(unsigned char* p, uint64_t n)
     {
-    const size_t ntiles = (size_t)((n + ROWS_TILE - 1) / ROWS_TILE);
+    const size_t ntiles = (size_t)((n + MIN_TILE - 1) / MIN_TILE);
     PassTables t;
     t.counts = (uint32_t*)p;
     t.row_total = (unsigned long long*)(p + align_up((size_t)RADIX * ntiles * 4, 256));
@@ -1052,8 +1371,10 @@ int dev_reorder_rows(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, ui
     uint32_t* ibuf[2] = { (uint32_t*)(p + 2 * arr), (uint32_t*)(p + 3 * arr) };
     const PassTables t = pass_tables_at(p + 4 * arr, n);
     KeyPlan plan;
+    phase_mark(0, st);
     if ((rc = key_census(n, keys, t, st, &plan)) != 0)
         return rc;
+    phase_mark(1, st);
     if (plan.npass == 0)
         {
         if (perm)
@@ -1068,6 +1389,96 @@ int dev_reorder_rows(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, ui
         return cudaGetLastError() == cudaSuccess ? 0 : -1;
         }
     const bool direct = plan.npass == 1; // one varying byte: the bucket pass is the whole sort
+    uint32_t row_words = perm ? 1u : 0u;
+    for (int i = 0; i < nfields; i++)
+        row_words += fields[i].row_bytes / 4;
+    const char* lay = getenv("PGSD_B200_BUCKET_LAYOUT");
+    if (!direct && row_words >= 1 && row_words <= AOS_MAX_ROW_WORDS && !(lay && !strcmp(lay, "soa")))
+        {
+        // ---- fast path: interleaved bucketed copy
+        const size_t aos_bytes = align_up((size_t)n * row_words * 4, 256);
+        void* rws = nullptr;
+        if ((rc = ws_reserve(g_rows_ws, 2 * arr + aos_bytes, &rws)) != 0)
+            return rc;
+        unsigned char* rp = (unsigned char*)rws;
+        uint32_t* keys_b = (uint32_t*)rp;
+        uint32_t* perm_b = (uint32_t*)(rp + arr);
+        uint32_t* aos = (uint32_t*)(rp + 2 * arr);
+        AosArgs aa;
+        memset(&aa, 0, sizeof(aa));
+        uint32_t off = 0;
+        int nf = 0;
+        for (int i = 0; i < nfields; i++)
+            {
+            aa.f[nf].in = (const uint32_t*)fields[i].in;
+            aa.f[nf].out = (uint32_t*)fields[i].out;
+            aa.f[nf].words = fields[i].row_bytes / 4;
+            aa.f[nf].off = off;
+            off += aa.f[nf].words;
+            nf++;
+            }
+        if (perm)
+            {
+            aa.f[nf].in = nullptr; // iota
+            aa.f[nf].out = perm;
+            aa.f[nf].words = 1;
+            aa.f[nf].off = off;
+            off += 1;
+            nf++;
+            }
+        aa.nfields = nf;
+        aa.row_words = row_words;
+        const int bshift = plan.topbit > 8 ? plan.topbit - 8 : 0;
+        const int items = row_words <= 10 ? 4 : (row_words <= 22 ? 2 : 1);
+        const uint32_t tile = (uint32_t)SORT_THREADS * items;
+        const uint32_t rtiles = (uint32_t)((n + tile - 1) / tile);
+        const bool m = rank_mode() == RANK_MATCH;
+        const size_t stage_b = (size_t)tile * row_words * 4;
+#define PGSD_LAUNCH_AOS(IT)                                                                                      \
+    {                                                                                                              \
+    k4_tile_histogram<IT><<<rtiles, SORT_THREADS, 0, st>>>(keys, n, bshift, rtiles, t.counts);                    \
+    k4_row_scan<<<RADIX, 256, 0, st>>>(t.counts, rtiles, t.row_total);                                            \
+    k4_digit_base<<<1, RADIX, 0, st>>>(t.row_total, t.digit_base);                                                \
+    if (m)                                                                                                         \
+        k4_bucket_aos<IT, RANK_MATCH><<<rtiles, SORT_THREADS, aos_smem_fixed<IT>() + stage_b, st>>>(              \
+            keys, keys_b, aos, n, bshift, rtiles, t.counts, t.digit_base, aa);                                     \
+    else                                                                                                           \
+        k4_bucket_aos<IT, RANK_BALLOT><<<rtiles, SORT_THREADS, aos_smem_fixed<IT>() + stage_b, st>>>(             \
+            keys, keys_b, aos, n, bshift, rtiles, t.counts, t.digit_base, aa);                                     \
+    }
+        if (items == 4)
+            PGSD_LAUNCH_AOS(4)
+        else if (items == 2)
+            PGSD_LAUNCH_AOS(2)
+        else
+            PGSD_LAUNCH_AOS(1)
+#undef PGSD_LAUNCH_AOS
+        dev_stats().kernel_launches += 4;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess)
+            {
+            set_last_error(std::string("reorder bucket pass: ") + cudaGetErrorString(e));
+            return -1;
+            }
+        phase_mark(2, st);
+        pair_passes(n, keys_b, keys_sorted, perm_b, plan, kbuf, ibuf, t, st);
+        phase_mark(3, st);
+        const uint64_t blocks = (n + GA_ROWS_PER_CTA - 1) / GA_ROWS_PER_CTA;
+        const size_t gsm = (size_t)GA_ROWS_PER_CTA * row_words * 4;
+        if (row_words % 2 == 0)
+            k5_gather_aos<2><<<(unsigned)blocks, GA_THREADS, gsm, st>>>(perm_b, n, aos, aa);
+        else
+            k5_gather_aos<1><<<(unsigned)blocks, GA_THREADS, gsm, st>>>(perm_b, n, aos, aa);
+        dev_stats().kernel_launches++;
+        phase_mark(4, st);
+        e = cudaGetLastError();
+        if (e != cudaSuccess)
+            {
+            set_last_error(std::string("reorder gather: ") + cudaGetErrorString(e));
+            return -1;
+            }
+        return 0;
+        }
     // bucketed copies: keys, original index (only if the caller wants perm), fields
     unsigned char* rp = nullptr;
     if (!direct)
@@ -1133,6 +1544,7 @@ int dev_reorder_rows(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, ui
         set_last_error(std::string("reorder bucket pass: ") + cudaGetErrorString(e));
         return -1;
         }
+    phase_mark(2, st);
     if (direct)
         return 0;
     pair_passes(n, keys_b, keys_sorted, perm_b, plan, kbuf, ibuf, t, st);
@@ -1142,7 +1554,10 @@ int dev_reorder_rows(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, ui
         set_last_error(std::string("reorder pair passes: ") + cudaGetErrorString(e));
         return -1;
         }
-    return dev_gather(n, perm_b, ngf, gf.data(), stream_v);
+    phase_mark(3, st);
+    rc = dev_gather(n, perm_b, ngf, gf.data(), stream_v);
+    phase_mark(4, st);
+    return rc;
     }
 
 int dev_gather(uint64_t n, const uint32_t* perm, int nfields, const ReorderField* fields, void* stream_v)

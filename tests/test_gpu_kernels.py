@@ -307,3 +307,24 @@ def test_sort_ids_rank_modes(cuda, monkeypatch, rank_mode):
     s, p = gpu_sort(cuda, keys)
     o = np.argsort(keys, kind='stable')
     assert (p == o.astype(np.uint32)).all() and (s == keys[o]).all()
+
+
+@pytest.mark.parametrize("widths,layout", [((16, 16), "aos"), ((16, 16, 16), "aos"), ((3, 1, 1), "soa"), ((2, 7, 1), "aos"),
+                                           ((1,), "aos"), ((3, 3, 1, 1, 1), "aos"), ((3, 3, 1, 1, 1), "soa")])
+def test_reorder_bucket_layouts_and_row_widths(cuda, monkeypatch, widths, layout):
+    """Interleaved (AoS) bucketed copy at 4/2/1 items per thread, its 40-word limit (wider rows take
+    the per-field copy), and the per-field layout forced by environment."""
+    monkeypatch.setenv("PGSD_B200_BUCKET_MIN_ROWS", "0")
+    monkeypatch.setenv("PGSD_B200_BUCKET_LAYOUT", layout)
+    rng = np.random.default_rng(sum(widths))
+    n = 50021
+    keys = rng.integers(0, 2 ** 18, size=n).astype(np.uint32)
+    fields = [rng.integers(0, 2 ** 32, size=(n, w), dtype=np.uint64).astype(np.uint32) for w in widths]
+    o = np.argsort(keys, kind='stable')
+    for want_perm in (True, False):
+        s, p, outs = _reorder_device_full(cuda, keys, fields, want_perm)
+        assert (s == keys[o]).all()
+        if want_perm:
+            assert (p == o.astype(np.uint32)).all()
+        for f, g in zip(fields, outs):
+            assert g.tobytes() == f[o].tobytes()
