@@ -795,7 +795,7 @@ constexpr int GA_THREADS = 128;
 constexpr int GA_CHUNKS = 4;
 constexpr int GA_ROWS_PER_CTA = (GA_THREADS / 32) * 32 * GA_CHUNKS;
 
-template <int VEC> // words per cp.async: 2 when RW is even and the copy is 8-byte aligned, else 1
+template <int VEC, bool PREFETCH> // VEC: words per cp.async, 2 when RW is even (8-byte aligned copies), else 1
 __global__ void __launch_bounds__(GA_THREADS)
     k5_gather_aos(const uint32_t* __restrict__ perm, uint64_t n, const uint32_t* __restrict__ aos,
                   const __grid_constant__ AosArgs args)
@@ -814,6 +814,19 @@ __global__ void __launch_bounds__(GA_THREADS)
         const uint64_t row0 = warp_row0 + 32 * g;
         rows[g] = row0 >= n ? 0u : (uint32_t)((n - row0) < 32 ? (n - row0) : 32);
         p[g] = lane < rows[g] ? ld_stream_u32(perm + row0 + lane) : 0u;
+        }
+    // Output rows [r0, r0+128) of this warp and source rows [r0, r0+128) of the bucketed copy lie in
+    // the same bucket(s): the warps that are resident together pull their bucket into L2 with
+    // sequential 128-byte prefetches, so that DRAM serves streams while the random reads below
+    // mostly hit L2 (random 32-byte sector reads alone hold DRAM at about 1/3 of its bandwidth).
+    if (PREFETCH)
+        {
+        const uint64_t b0 = warp_row0 * RW * 4;
+        const uint64_t last = warp_row0 + 32 * GA_CHUNKS < n ? warp_row0 + 32 * GA_CHUNKS : n;
+        const uint64_t b1 = last * RW * 4;
+        const char* base = reinterpret_cast<const char*>(aos);
+        for (uint64_t b = (b0 & ~127ull) + (uint64_t)lane * 128; b < b1; b += 32 * 128)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(base + b));
         }
     const uint32_t RV = RW / VEC; // copies per row
 #pragma unroll
@@ -1117,8 +1130,10 @@ static int sort_setup()
         cudaFuncSetAttribute(k4_bucket_aos<4, RANK_MATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
         cudaFuncSetAttribute(k4_bucket_aos<2, RANK_MATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
         cudaFuncSetAttribute(k4_bucket_aos<1, RANK_MATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-        cudaFuncSetAttribute(k5_gather_aos<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-        cudaFuncSetAttribute(k5_gather_aos<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(k5_gather_aos<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(k5_gather_aos<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(k5_gather_aos<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(k5_gather_aos<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
         attr_done = true;
         }
     if (!g_census_host && cudaHostAlloc((void**)&g_census_host, 4 * RADIX * 8, cudaHostAllocDefault) != cudaSuccess)
@@ -1465,10 +1480,22 @@ int dev_reorder_rows(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, ui
         phase_mark(3, st);
         const uint64_t blocks = (n + GA_ROWS_PER_CTA - 1) / GA_ROWS_PER_CTA;
         const size_t gsm = (size_t)GA_ROWS_PER_CTA * row_words * 4;
+        const char* pf = getenv("PGSD_B200_GATHER_PREFETCH");
+        const bool prefetch = !(pf && pf[0] == '0');
         if (row_words % 2 == 0)
-            k5_gather_aos<2><<<(unsigned)blocks, GA_THREADS, gsm, st>>>(perm_b, n, aos, aa);
+            {
+            if (prefetch)
+                k5_gather_aos<2, true><<<(unsigned)blocks, GA_THREADS, gsm, st>>>(perm_b, n, aos, aa);
+            else
+                k5_gather_aos<2, false><<<(unsigned)blocks, GA_THREADS, gsm, st>>>(perm_b, n, aos, aa);
+            }
         else
-            k5_gather_aos<1><<<(unsigned)blocks, GA_THREADS, gsm, st>>>(perm_b, n, aos, aa);
+            {
+            if (prefetch)
+                k5_gather_aos<1, true><<<(unsigned)blocks, GA_THREADS, gsm, st>>>(perm_b, n, aos, aa);
+            else
+                k5_gather_aos<1, false><<<(unsigned)blocks, GA_THREADS, gsm, st>>>(perm_b, n, aos, aa);
+            }
         dev_stats().kernel_launches++;
         phase_mark(4, st);
         e = cudaGetLastError();
