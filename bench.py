@@ -566,11 +566,8 @@ def main():
     windows = []
     rd = run_read_leg(lib, dist, args, peaks, windows)   # communicator: "single" (frames are independent)
     if dist.world > 1:
-        uid = C.create_string_buffer(128)
-        if dist.rank == 0:
-            _lib.check(lib.pgsd_b200_nccl_unique_id(uid), "nccl_unique_id")
-        raw = dist.bcast_bytes(uid.raw, 128)
-        _lib.check(lib.pgsd_b200_comm_init_nccl(dist.rank, dist.world, raw, dist.local), "comm_init_nccl")
+        from pgsd_sph_b200 import comm
+        comm.init_nccl(dist.rank, dist.world, dist.bcast_bytes, dist.local)
     wr = run_write_leg(lib, dist, args, peaks, windows)
     sampler.stop()
 

@@ -17,6 +17,7 @@
 #include <deque>
 #include <dlfcn.h>
 #include <errno.h>
+#include <map>
 #include <mutex>
 #include <thread>
 #include <fcntl.h>
@@ -127,9 +128,6 @@ struct Ctx
     std::vector<ArenaFrame*> frames;
     ArenaFrame* cur = nullptr;
 
-    // read path
-    char* read_buf[2] = { nullptr, nullptr };
-    cudaEvent_t read_ev[2] = { nullptr, nullptr };
 
     // reorder_host scratch
     char* scratch = nullptr;
@@ -461,6 +459,12 @@ int dev_init(int device)
     return 0;
     }
 
+namespace
+    {
+void readers_release();
+void cache_release_all();
+    }
+
 void dev_shutdown()
     {
     if (!g.inited)
@@ -477,15 +481,8 @@ void dev_shutdown()
         }
     g.frames.clear();
     g.cur = nullptr;
-    for (int i = 0; i < 2; i++)
-        {
-        if (g.read_buf[i])
-            cudaFreeHost(g.read_buf[i]);
-        if (g.read_ev[i])
-            cudaEventDestroy(g.read_ev[i]);
-        g.read_buf[i] = nullptr;
-        g.read_ev[i] = nullptr;
-        }
+    readers_release();
+    cache_release_all();
     if (g.scratch)
         cudaFree(g.scratch);
     g.scratch = nullptr;
@@ -715,43 +712,129 @@ int dev_copy_to_host(void* host_dst, const void* dev_src, uint64_t bytes)
     return 0;
     }
 
+// file -> pinned -> device.  Large reads are split into 4 MiB pieces over 8 reader threads, each with
+// its own pair of pinned buffers and copy stream: page-cache reads of one file scale with threads
+// (no exclusive inode lock on the read side) and overlap the H2D DMA of the previous pieces.
+namespace
+    {
+constexpr uint64_t READ_PIECE = 4ull << 20;
+constexpr int READ_THREADS = 8;
+struct Reader
+    {
+    char* buf[2] = { nullptr, nullptr };
+    cudaEvent_t ev[2] = { nullptr, nullptr };
+    cudaStream_t st = nullptr;
+    };
+Reader g_readers[READ_THREADS];
+bool g_readers_ready = false;
+
+int readers_init()
+    {
+    if (g_readers_ready)
+        return 0;
+    for (int i = 0; i < READ_THREADS; i++)
+        {
+        Reader& r = g_readers[i];
+        CUDA_TRY(cudaStreamCreateWithFlags(&r.st, cudaStreamNonBlocking), -1);
+        for (int k = 0; k < 2; k++)
+            {
+            CUDA_TRY(cudaHostAlloc((void**)&r.buf[k], READ_PIECE, cudaHostAllocDefault), -6);
+            CUDA_TRY(cudaEventCreateWithFlags(&r.ev[k], cudaEventDisableTiming), -1);
+            }
+        }
+    g_readers_ready = true;
+    return 0;
+    }
+
+void readers_release()
+    {
+    for (int i = 0; i < READ_THREADS; i++)
+        {
+        Reader& r = g_readers[i];
+        for (int k = 0; k < 2; k++)
+            {
+            if (r.buf[k])
+                cudaFreeHost(r.buf[k]);
+            if (r.ev[k])
+                cudaEventDestroy(r.ev[k]);
+            r.buf[k] = nullptr;
+            r.ev[k] = nullptr;
+            }
+        if (r.st)
+            cudaStreamDestroy(r.st);
+        r.st = nullptr;
+        }
+    g_readers_ready = false;
+    }
+
+// pieces t, t+T, t+2T, ... of the read
+bool reader_run(int t, int T, int fd, char* dev_dst, uint64_t bytes, uint64_t file_off)
+    {
+    cudaSetDevice(g.device);
+    Reader& r = g_readers[t];
+    const uint64_t npieces = (bytes + READ_PIECE - 1) / READ_PIECE;
+    int k = 0;
+    bool ok = true;
+    for (uint64_t i = (uint64_t)t; ok && i < npieces; i += (uint64_t)T)
+        {
+        const uint64_t off = i * READ_PIECE;
+        const uint64_t len = bytes - off < READ_PIECE ? bytes - off : READ_PIECE;
+        ok = cudaEventSynchronize(r.ev[k]) == cudaSuccess;
+        uint64_t got = 0;
+        while (ok && got < len)
+            {
+            ssize_t n = pread(fd, r.buf[k] + got, len - got, (off_t)(file_off + off + got));
+            if (n < 0 && errno == EINTR)
+                continue;
+            if (n <= 0)
+                ok = false;
+            else
+                got += (uint64_t)n;
+            }
+        ok = ok && cudaMemcpyAsync(dev_dst + off, r.buf[k], len, cudaMemcpyHostToDevice, r.st) == cudaSuccess
+             && cudaEventRecord(r.ev[k], r.st) == cudaSuccess;
+        k ^= 1;
+        }
+    return cudaStreamSynchronize(r.st) == cudaSuccess && ok;
+    }
+    } // namespace
+
 int dev_read_file_to_device(int fd, void* dev_dst, uint64_t bytes, uint64_t file_off)
     {
     int rc = dev_init(-1);
     if (rc != 0)
         return rc;
-    for (int i = 0; i < 2; i++)
-        if (!g.read_buf[i])
-            {
-            CUDA_TRY(cudaHostAlloc((void**)&g.read_buf[i], g.slot_bytes, cudaHostAllocDefault), -6);
-            CUDA_TRY(cudaEventCreateWithFlags(&g.read_ev[i], cudaEventDisableTiming), -1);
-            }
-    uint64_t done = 0;
-    int k = 0;
-    while (done < bytes)
+    if (bytes == 0)
+        return 0;
+    rc = readers_init();
+    if (rc != 0)
+        return rc;
+    const uint64_t npieces = (bytes + READ_PIECE - 1) / READ_PIECE;
+    const int T = npieces < (uint64_t)READ_THREADS ? (int)npieces : READ_THREADS;
+    bool ok = true;
+    if (T == 1)
+        ok = reader_run(0, 1, fd, (char*)dev_dst, bytes, file_off);
+    else
         {
-        uint64_t len = bytes - done < g.slot_bytes ? bytes - done : g.slot_bytes;
-        CUDA_TRY(cudaEventSynchronize(g.read_ev[k]), -1);
-        uint64_t got = 0;
-        while (got < len)
-            {
-            ssize_t r = pread(fd, g.read_buf[k] + got, len - got, (off_t)(file_off + done + got));
-            if (r < 0 && errno == EINTR)
-                continue;
-            if (r <= 0)
-                {
-                set_last_error("pread failed or hit end of file");
-                return -1;
-                }
-            got += (uint64_t)r;
-            }
-        CUDA_TRY(cudaMemcpyAsync((char*)dev_dst + done, g.read_buf[k], len, cudaMemcpyHostToDevice, g.copy[k]), -1);
-        CUDA_TRY(cudaEventRecord(g.read_ev[k], g.copy[k]), -1);
-        done += len;
-        k ^= 1;
+        std::vector<std::thread> th;
+        std::atomic<bool> all_ok { true };
+        for (int t = 1; t < T; t++)
+            th.emplace_back([&, t]() {
+                if (!reader_run(t, T, fd, (char*)dev_dst, bytes, file_off))
+                    all_ok = false;
+            });
+        if (!reader_run(0, T, fd, (char*)dev_dst, bytes, file_off))
+            all_ok = false;
+        for (auto& x : th)
+            x.join();
+        ok = all_ok.load();
         }
-    CUDA_TRY(cudaStreamSynchronize(g.copy[0]), -1);
-    CUDA_TRY(cudaStreamSynchronize(g.copy[1]), -1);
+    if (!ok)
+        {
+        set_last_error("reading the file into device memory failed (pread or H2D copy)");
+        cudaGetLastError();
+        return -1;
+        }
     g_stats.h2d_bytes += bytes;
     g_stats.file_bytes_read += bytes;
     return 0;
@@ -1086,18 +1169,86 @@ int dev_reorder_host(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, ui
     }
 
 // ------------------------------------------------------------------------------ helpers
+// Caching allocator behind pgsd_b200_malloc/free: per-frame device arrays of the read path
+// (6 chunks in, 6 out, ids) are recycled instead of paying cudaMalloc + the device-wide
+// synchronisation of cudaFree every frame.  Sizes are rounded up to 2 MiB; at most 16 GiB is cached.
+namespace
+    {
+std::mutex g_cache_mu;
+std::map<uint64_t, std::vector<void*>> g_cache_free;
+std::map<void*, uint64_t> g_cache_size;
+uint64_t g_cache_bytes = 0;
+constexpr uint64_t CACHE_MAX = 16ull << 30;
+uint64_t cache_round(uint64_t b)
+    {
+    if (b == 0)
+        b = 1;
+    const uint64_t q = b < (1ull << 20) ? 512 : (2ull << 20);
+    return (b + q - 1) / q * q;
+    }
+void cache_release_all()
+    {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    for (auto& kv : g_cache_free)
+        for (void* p : kv.second)
+            {
+            cudaFree(p);
+            g_cache_size.erase(p);
+            }
+    g_cache_free.clear();
+    g_cache_bytes = 0;
+    }
+    } // namespace
+
 int dev_malloc(void** p, uint64_t bytes)
     {
     int rc = dev_init(-1);
     if (rc != 0)
         return rc;
-    CUDA_TRY(cudaMalloc(p, bytes ? bytes : 1), -6);
+    const uint64_t sz = cache_round(bytes);
+        {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        auto it = g_cache_free.find(sz);
+        if (it != g_cache_free.end() && !it->second.empty())
+            {
+            *p = it->second.back();
+            it->second.pop_back();
+            g_cache_bytes -= sz;
+            return 0;
+            }
+        }
+    if (cudaMalloc(p, sz) != cudaSuccess)
+        {
+        cudaGetLastError();
+        cache_release_all(); // give cached blocks back and retry once
+        CUDA_TRY(cudaMalloc(p, sz), -6);
+        }
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    g_cache_size[*p] = sz;
     return 0;
     }
 int dev_free(void* p)
     {
-    if (p)
+    if (!p)
+        return 0;
+    // the block may be handed out again at once: everything queued on the caller's stream that
+    // could still touch it must have finished (what cudaFree guarantees implicitly)
+    CUDA_TRY(cudaStreamSynchronize(g.user), -1);
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    auto it = g_cache_size.find(p);
+    if (it == g_cache_size.end())
+        {
         CUDA_TRY(cudaFree(p), -1);
+        return 0;
+        }
+    if (g_cache_bytes + it->second > CACHE_MAX)
+        {
+        g_cache_size.erase(it);
+        CUDA_TRY(cudaFree(p), -1);
+        return 0;
+        }
+    g_cache_free[it->second].push_back(p);
+    g_cache_bytes += it->second;
     return 0;
     }
 int dev_host_alloc(void** p, uint64_t bytes)

@@ -102,6 +102,82 @@ class PinnedArray:
             pass
 
 
+class _PinnedBlock:
+    """One page-locked allocation; goes back to its pool when the last numpy view of it dies."""
+
+    def __init__(self, pool, ptr, nbytes):
+        self.pool, self.ptr, self.nbytes = pool, ptr, nbytes
+
+    def __del__(self):
+        try:
+            self.pool._give_back(self.ptr, self.nbytes)
+        except Exception:
+            pass
+
+
+class PinnedPool:
+    """Recycling allocator of page-locked numpy arrays.
+
+    ``cudaHostAlloc`` and first-touch page faults cost more than the D2H copy of a frame, so the
+    arrays a reordered frame is returned in come from here: when the caller drops a frame (e.g. the
+    loop variable of ``for frame in trajectory`` is rebound) its buffers are reused for the next one.
+    """
+
+    def __init__(self, max_cached_bytes=16 << 30):
+        self._free = {}
+        self._cached = 0
+        self._max = int(max_cached_bytes)
+
+    def empty(self, shape, dtype):
+        dtype = np.dtype(dtype)
+        shape = tuple(int(x) for x in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+        count = int(np.prod(shape)) if shape else 1
+        nbytes = max(count * dtype.itemsize, 1)
+        lst = self._free.get(nbytes)
+        if lst:
+            ptr = lst.pop()
+            self._cached -= nbytes
+        else:
+            p = C.c_void_p()
+            _lib.check(_lib.load().pgsd_b200_host_alloc(C.byref(p), nbytes), "pgsd_b200_host_alloc")
+            ptr = p.value
+        buf = (C.c_char * nbytes).from_address(ptr)
+        buf._block = _PinnedBlock(self, ptr, nbytes)  # numpy's memoryview keeps buf (and the block) alive
+        return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+
+    def _give_back(self, ptr, nbytes):
+        if self._cached + nbytes <= self._max:
+            self._free.setdefault(nbytes, []).append(ptr)
+            self._cached += nbytes
+        else:
+            _lib.load().pgsd_b200_host_free(ptr)
+
+    def clear(self):
+        lib = _lib.load()
+        for lst in self._free.values():
+            for ptr in lst:
+                lib.pgsd_b200_host_free(ptr)
+        self._free, self._cached = {}, 0
+
+
+_default_pool = None
+
+
+def pinned_pool():
+    global _default_pool
+    if _default_pool is None:
+        _default_pool = PinnedPool()
+    return _default_pool
+
+
+def download(dev, pool=None):
+    """DeviceArray -> numpy array in pooled page-locked memory (one DMA, no staging copy)."""
+    out = (pool or pinned_pool()).empty(dev.shape, dev.dtype)
+    if dev.nbytes:
+        _lib.check(_lib.load().pgsd_b200_memcpy(out.ctypes.data, dev.ptr, dev.nbytes, D2H), "D2H copy")
+    return out
+
+
 # ---- DLPack (v0.x capsule "dltensor") -------------------------------------------------------
 class _DLDevice(C.Structure):
     _fields_ = [("device_type", C.c_int), ("device_id", C.c_int)]

@@ -293,6 +293,9 @@ class HOOMDTrajectory(object):
         self._initial_frame = None
         self._reorder = reorder
         self._device = bool(device)
+        # reorder='id': per-particle chunks go file -> pinned -> HBM directly (no host array in between),
+        # are sorted + gathered there, and come back with one D2H copy per field
+        self._read_device = self._device or reorder == 'id'
         logger.info('opening HOOMDTrajectory: ' + str(self.file))
         if self.file.schema != 'hoomd':
             raise RuntimeError('PGSD file is not a hoomd schema file: ' + str(self.file))
@@ -436,7 +439,7 @@ class HOOMDTrajectory(object):
                 if name in ('N', 'types', 'type_shapes'):
                     continue
                 if self.file.chunk_exists(frame=idx, name=path + '/' + name, write_all=False):
-                    dev = self._device and path == 'particles'
+                    dev = self._read_device and path == 'particles'
                     container.__dict__[name] = self.file.read_chunk(frame=idx, name=path + '/' + name,
                                                                     offset=0, r_all=False, device=dev)
                     if path == 'particles':
@@ -457,7 +460,7 @@ class HOOMDTrajectory(object):
 
         for log in self.file.find_matching_chunk_names('log/', False):
             if self.file.chunk_exists(frame=idx, name=log, write_all=False):
-                dev = self._device and log.startswith('log/particles/')
+                dev = self._read_device and log.startswith('log/particles/')
                 snap.log[log[4:]] = self.file.read_chunk(frame=idx, name=log, offset=0, r_all=False, device=dev)
             elif self._initial_frame is not None and log[4:] in self._initial_frame.log:
                 snap.log[log[4:]] = self._initial_frame.log[log[4:]]
@@ -494,11 +497,19 @@ class HOOMDTrajectory(object):
                 todo['l:' + k] = v
             else:
                 out.log[k] = v
-        mixed = self._device and any(not is_device_array(v) for v in todo.values())
-        if mixed:
+        if self._read_device:
             # frame-0 fallbacks held on the host: upload so one device gather covers everything
             todo = {k: (v if is_device_array(v) else DeviceArray.from_numpy(v)) for k, v in todo.items()}
-        sorted_ids, res = reorder_by_id(ids, todo, device=self._device)
+            if not is_device_array(ids):
+                ids = DeviceArray.from_numpy(numpy.ascontiguousarray(ids, dtype=numpy.uint32))
+        sorted_ids, res = reorder_by_id(ids, todo, device=self._read_device)
+        if self._read_device and not self._device:
+            from .devmem import download
+            host = {k: download(v) for k, v in res.items()}
+            sorted_host = download(sorted_ids)
+            for v in list(res.values()) + [sorted_ids]:
+                v.free()
+            sorted_ids, res = sorted_host, host
         out.log[ID_CHUNK[4:]] = sorted_ids
         for k, v in res.items():
             if k[0] == 'p':
