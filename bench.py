@@ -307,16 +307,21 @@ def run_read_leg(lib, dist, args, peaks, windows):
         p = fr.particles
         return p.position, p.velocity, p.typeid, p.density, p.pressure, fr.log['particles/id']
 
+    out = None
     for i in range(args.warmup):
-        step_e2e(i)
+        out = step_e2e(i)  # held like in the timed loop: two generations of pooled pinned arrays
     lib.pgsd_b200_reset_stats()
     dist.barrier()
     lib.pgsd_b200_synchronize()
     w0 = time.perf_counter()
+    step_t = []
     for i in range(args.steps):
+        ts = time.perf_counter()
         out = step_e2e(i)
+        step_t.append(time.perf_counter() - ts)
     lib.pgsd_b200_synchronize()
     t_e2e = time.perf_counter() - w0
+    log(f"[rank {dist.rank}] read e2e per-step ms: " + " ".join(f"{1e3 * x:.1f}" for x in step_t))
     dist.barrier()
     windows.append((w0, time.perf_counter()))
     assert out[5][0] == 0 and out[5][-1] == n - 1
@@ -376,18 +381,17 @@ def run_write_leg(lib, dist, args, peaks, windows):
         f = fl.open(path, 'w', 'pgsd-b200', 'hoomd', [1, 4])
         prep = f.prepare_frame_soa([(nm, [src[j] for j in idx], dt, rows, True) for nm, idx, dt in SOA_CHUNKS],
                                    rank=dist.rank)
-        tm = Timer(lib)
         k1_ms = []
+        lib.pgsd_b200_pack_profiling(1 if leg == "device" else 0)
 
         def step(i, timed=False):
             for k, a in synth.frame_scalars(n_total, i):
                 f.write_chunk(k, a, write_all=False)
+            f.write_frame_soa(prep)
             if timed and leg == "device":
-                tm.start()
-                f.write_frame_soa(prep)
-                k1_ms.append(tm.stop())
-            else:
-                f.write_frame_soa(prep)
+                ms = C.c_float()
+                if lib.pgsd_b200_pack_last_ms(C.byref(ms)) == 0:  # CUDA events around the K1 launch
+                    k1_ms.append(float(ms.value))
             f.end_frame()
 
         for i in range(args.warmup):
@@ -406,6 +410,7 @@ def run_write_leg(lib, dist, args, peaks, windows):
         windows.append((w0, time.perf_counter()))
         st = get_stats(lib)
         dt = dist.max(dt)
+        lib.pgsd_b200_pack_profiling(0)
         f.close()
         size = os.path.getsize(path) if dist.rank == 0 else 0
         result[leg] = {"s": dt, "GBps": payload * args.steps / dt / 1e9, "stats": st, "k1_ms": k1_ms,

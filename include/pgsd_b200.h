@@ -191,6 +191,10 @@ int pgsd_b200_flush_l2(void);
    (CUDA events on the caller's stream): out4 = {key census, bucket pass, pair passes, gather} in ms.
    Measurement hook for bench.py; off by default. */
 int pgsd_b200_reorder_profiling(int on);
+/* Device time of the K1 launch of the last pgsd_b200_write_chunk(s)_soa / device pgsd_write_chunk
+   (CUDA events recorded on the caller's stream directly around the launch). */
+int pgsd_b200_pack_profiling(int on);
+int pgsd_b200_pack_last_ms(float* ms);
 int pgsd_b200_reorder_phase_ms(float* out4);
 
 #ifdef __cplusplus

@@ -191,6 +191,8 @@ SIGNATURES = {
     "pgsd_b200_timer_stop": (_i, [_vp, C.POINTER(C.c_float)]),
     "pgsd_b200_timer_destroy": (_i, [_vp]),
     "pgsd_b200_flush_l2": (_i, []),
+    "pgsd_b200_pack_profiling": (_i, [_i]),
+    "pgsd_b200_pack_last_ms": (_i, [C.POINTER(C.c_float)]),
     "pgsd_b200_reorder_profiling": (_i, [_i]),
     "pgsd_b200_reorder_phase_ms": (_i, [C.POINTER(C.c_float)]),
 }

@@ -323,6 +323,12 @@ int pgsd_b200_timer_start(void* t) { return dev_timer_start(t); }
 int pgsd_b200_timer_stop(void* t, float* ms) { return dev_timer_stop(t, ms); }
 int pgsd_b200_timer_destroy(void* t) { return dev_timer_destroy(t); }
 int pgsd_b200_flush_l2(void) { return dev_flush_l2(); }
+int pgsd_b200_pack_profiling(int on)
+    {
+    dev_pack_profiling(on != 0);
+    return 0;
+    }
+int pgsd_b200_pack_last_ms(float* ms) { return ms ? dev_pack_last_ms(ms) : PGSD_ERROR_INVALID_ARGUMENT; }
 int pgsd_b200_reorder_profiling(int on)
     {
     dev_reorder_profiling(on != 0);

@@ -572,6 +572,24 @@ int dev_pack(void* dst_dev, int dst_type, uint64_t N, uint32_t M, int src_type, 
     return pack_launch(&s, 1, (cudaStream_t)stream);
     }
 
+// optional CUDA-event timing of the last K1 launch issued by a frame write (bench.py)
+static bool g_pack_prof = false, g_pack_timed = false;
+static cudaEvent_t g_pack_ev[2] = { nullptr, nullptr };
+void dev_pack_profiling(bool on)
+    {
+    g_pack_prof = on;
+    g_pack_timed = false;
+    }
+int dev_pack_last_ms(float* ms)
+    {
+    *ms = 0.f;
+    if (!g_pack_timed)
+        return -2;
+    CUDA_TRY(cudaEventSynchronize(g_pack_ev[1]), -1);
+    CUDA_TRY(cudaEventElapsedTime(ms, g_pack_ev[0], g_pack_ev[1]), -1);
+    return 0;
+    }
+
 int dev_arena_pack(PackRequest* reqs, int n)
     {
     int rc = dev_init(-1);
@@ -636,9 +654,23 @@ int dev_arena_pack(PackRequest* reqs, int n)
                 return rc;
             ns++;
             }
+        if (g_pack_prof)
+            {
+            if (!g_pack_ev[0])
+                {
+                cudaEventCreate(&g_pack_ev[0]);
+                cudaEventCreate(&g_pack_ev[1]);
+                }
+            cudaEventRecord(g_pack_ev[0], g.user);
+            }
         rc = pack_launch(segs, ns, g.user);
         if (rc != 0)
             return rc;
+        if (g_pack_prof)
+            {
+            cudaEventRecord(g_pack_ev[1], g.user);
+            g_pack_timed = true;
+            }
         }
     if (need_sync)
         {

@@ -98,6 +98,8 @@ int dev_reorder_host(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, ui
                      int nfields, const ReorderField* fields);
 
 // phase timing of the last bucketed reorder (CUDA events): census, bucket pass, pair passes, gather
+void dev_pack_profiling(bool on); // K1 launch of the last frame write
+int dev_pack_last_ms(float* ms);
 void dev_reorder_profiling(bool on);
 int dev_reorder_phase_ms(float* out4);
 
