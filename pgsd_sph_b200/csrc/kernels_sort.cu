@@ -30,6 +30,7 @@ constexpr int SORT_THREADS = 512;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int SORT_ITEMS = 16;
 constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS; // 8192 keys per CTA (pair passes)
+constexpr int PADDED_TILE = SORT_TILE + SORT_TILE / 32;
 constexpr int ROWS_ITEMS = 8;
 constexpr int ROWS_TILE = SORT_THREADS * ROWS_ITEMS; // 4096 rows per CTA (bucket pass with payload)
 
@@ -343,10 +344,12 @@ __global__ void __launch_bounds__(SORT_THREADS)
                const unsigned long long* __restrict__ digit_base)
     {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint32_t* skeys = reinterpret_cast<uint32_t*>(smem_raw); // SORT_TILE
-    uint32_t* sidx = skeys + SORT_TILE;                       // SORT_TILE
+    // one pad word per 32: with exactly 32 keys per digit in a tile (dense ids in the later passes)
+    // the 32 lanes of a warp would otherwise all store to positions 32*d + c, i.e. one bank
+    uint32_t* skeys = reinterpret_cast<uint32_t*>(smem_raw); // PADDED_TILE
+    uint32_t* sidx = skeys + PADDED_TILE;                     // PADDED_TILE
     TileRankSmem sm;
-    sm.whist = sidx + SORT_TILE;
+    sm.whist = sidx + PADDED_TILE;
     sm.dstart = sm.whist + SORT_WARPS * RADIX;
     sm.gdelta = reinterpret_cast<unsigned long long*>(sm.dstart + RADIX);
     __shared__ uint32_t wtot[8];
@@ -383,8 +386,9 @@ __global__ void __launch_bounds__(SORT_THREADS)
         const uint32_t e = wbase + k * 32 + lane;
         if (e < tile_n)
             {
-            skeys[pos[k]] = key[k];
-            sidx[pos[k]] = src[k];
+            const uint32_t pp = pos[k] + (pos[k] >> 5);
+            skeys[pp] = key[k];
+            sidx[pp] = src[k];
             }
         }
     __syncthreads();
@@ -395,16 +399,17 @@ __global__ void __launch_bounds__(SORT_THREADS)
         const uint32_t j = tid + k * SORT_THREADS;
         if (j < tile_n)
             {
-            const uint32_t kv = skeys[j];
+            const uint32_t jp = j + (j >> 5);
+            const uint32_t kv = skeys[jp];
             const unsigned long long g = sm.gdelta[(kv >> shift) & 255u] + j;
             keys_out[g] = kv;
-            idx_out[g] = sidx[j];
+            idx_out[g] = sidx[jp];
             }
         }
     }
 
 constexpr size_t SCATTER_SMEM
-    = (size_t)(2 * SORT_TILE + SORT_WARPS * RADIX + RADIX) * sizeof(uint32_t) + RADIX * sizeof(unsigned long long);
+    = (size_t)(2 * PADDED_TILE + SORT_WARPS * RADIX + RADIX) * sizeof(uint32_t) + RADIX * sizeof(unsigned long long);
 
 // ---- bucket pass: the same stable partition, carrying whole rows ---------------------------------
 // Groups the rows of every field by the top 8 significant key bits so that the permutation gather
@@ -631,6 +636,51 @@ struct AosArgs
     uint32_t row_words; // RW
     };
 
+// One field of a full, 16-byte aligned tile -> interleaved rows in shared memory.  WC > 0: W is the
+// compile-time constant WC (divisions fold into multiplies); WC == 0: runtime W.
+template <int TILE, int WC>
+__device__ __forceinline__ void stage_field_vec(const uint4* __restrict__ in4, uint32_t W_rt, uint32_t RW, uint32_t off,
+                                                const uint16_t* __restrict__ spos, uint32_t* __restrict__ stage)
+    {
+    const uint32_t W = WC > 0 ? (uint32_t)WC : W_rt;
+    const int tid = threadIdx.x;
+    const uint32_t nvec = (uint32_t)TILE * W / 4;
+    for (uint32_t v0 = 0; v0 < nvec; v0 += 4 * SORT_THREADS)
+        {
+        uint4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            {
+            const uint32_t vq = v0 + tid + k * SORT_THREADS;
+            if (vq < nvec)
+                v[k] = ldg_stream_v4(in4 + vq);
+            }
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            {
+            const uint32_t vq = v0 + tid + k * SORT_THREADS;
+            if (vq < nvec)
+                {
+                const uint32_t words[4] = { v[k].x, v[k].y, v[k].z, v[k].w };
+                uint32_t e = (vq * 4) / W, c = vq * 4 - e * W;
+                uint32_t base = (uint32_t)spos[e] * RW + off;
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    {
+                    stage[base + c] = words[u];
+                    if (++c == W)
+                        {
+                        c = 0;
+                        e++;
+                        if (u < 3)
+                            base = (uint32_t)spos[e] * RW + off;
+                        }
+                    }
+                }
+            }
+        }
+    }
+
 template <int ITEMS, int RM>
 __global__ void __launch_bounds__(SORT_THREADS)
     k4_bucket_aos(const uint32_t* __restrict__ keys_in, uint32_t* __restrict__ keys_out, uint32_t* __restrict__ aos_out,
@@ -691,37 +741,13 @@ __global__ void __launch_bounds__(SORT_THREADS)
         if (tile_n == TILE && (reinterpret_cast<uintptr_t>(in) & 15u) == 0)
             {
             const uint4* in4 = reinterpret_cast<const uint4*>(in);
-            const uint32_t nvec = total / 4; // TILE * W / 4, a multiple of SORT_THREADS * ITEMS / 4
-            for (uint32_t v0 = 0; v0 < nvec; v0 += 4 * SORT_THREADS)
+            switch (W)
                 {
-                uint4 v[4];
-#pragma unroll
-                for (int k = 0; k < 4; k++)
-                    {
-                    const uint32_t vq = v0 + tid + k * SORT_THREADS;
-                    if (vq < nvec)
-                        v[k] = ldg_stream_v4(in4 + vq);
-                    }
-#pragma unroll
-                for (int k = 0; k < 4; k++)
-                    {
-                    const uint32_t vq = v0 + tid + k * SORT_THREADS;
-                    if (vq < nvec)
-                        {
-                        const uint32_t words[4] = { v[k].x, v[k].y, v[k].z, v[k].w };
-                        uint32_t e = (vq * 4) / W, c = vq * 4 - e * W;
-#pragma unroll
-                        for (int u = 0; u < 4; u++)
-                            {
-                            stage[(uint32_t)spos[e] * RW + f.off + c] = words[u];
-                            if (++c == W)
-                                {
-                                c = 0;
-                                e++;
-                                }
-                            }
-                        }
-                    }
+                case 1: stage_field_vec<TILE, 1>(in4, W, RW, f.off, spos, stage); break;
+                case 2: stage_field_vec<TILE, 2>(in4, W, RW, f.off, spos, stage); break;
+                case 3: stage_field_vec<TILE, 3>(in4, W, RW, f.off, spos, stage); break;
+                case 4: stage_field_vec<TILE, 4>(in4, W, RW, f.off, spos, stage); break;
+                default: stage_field_vec<TILE, 0>(in4, W, RW, f.off, spos, stage); break;
                 }
             }
         else
@@ -763,19 +789,44 @@ __global__ void __launch_bounds__(SORT_THREADS)
                 }
             }
         }
-    const uint32_t total_out = tile_n * RW;
-    uint32_t j = tid / RW, c = tid - j * RW;
-    const uint32_t dj = SORT_THREADS / RW, dc = SORT_THREADS - dj * RW;
-    for (uint32_t q = tid; q < total_out; q += SORT_THREADS)
+    if ((RW & 1u) == 0)
         {
-        const unsigned long long g = sm.gdelta[(skeys[j] >> shift) & 255u] + j;
-        aos_out[g * RW + c] = stage[q];
-        j += dj;
-        c += dc;
-        if (c >= RW)
+        // rows are 8-byte multiples: move them as 64-bit pieces (half the instructions per byte)
+        const uint32_t R2 = RW / 2;
+        const uint32_t total2 = tile_n * R2;
+        const uint2* stage2 = reinterpret_cast<const uint2*>(stage);
+        uint2* out2 = reinterpret_cast<uint2*>(aos_out);
+        uint32_t j = tid / R2, c = tid - j * R2;
+        const uint32_t dj = SORT_THREADS / R2, dc = SORT_THREADS - dj * R2;
+        for (uint32_t q = tid; q < total2; q += SORT_THREADS)
             {
-            c -= RW;
-            j++;
+            const unsigned long long g = sm.gdelta[(skeys[j] >> shift) & 255u] + j;
+            out2[g * R2 + c] = stage2[q];
+            j += dj;
+            c += dc;
+            if (c >= R2)
+                {
+                c -= R2;
+                j++;
+                }
+            }
+        }
+    else
+        {
+        const uint32_t total_out = tile_n * RW;
+        uint32_t j = tid / RW, c = tid - j * RW;
+        const uint32_t dj = SORT_THREADS / RW, dc = SORT_THREADS - dj * RW;
+        for (uint32_t q = tid; q < total_out; q += SORT_THREADS)
+            {
+            const unsigned long long g = sm.gdelta[(skeys[j] >> shift) & 255u] + j;
+            aos_out[g * RW + c] = stage[q];
+            j += dj;
+            c += dc;
+            if (c >= RW)
+                {
+                c -= RW;
+                j++;
+                }
             }
         }
     }
