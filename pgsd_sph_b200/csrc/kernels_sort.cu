@@ -337,7 +337,7 @@ __device__ __forceinline__ void tile_rank(const uint32_t (&key)[ITEMS], uint32_t
 
 // pair pass.  FIRST: the index payload is implicit (idx = global position), saving its read.
 template <bool FIRST, int RM>
-__global__ void __launch_bounds__(SORT_THREADS)
+__global__ void __launch_bounds__(SORT_THREADS, 2)
     k4_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ idx_in,
                uint32_t* __restrict__ keys_out, uint32_t* __restrict__ idx_out, uint64_t n, int shift,
                uint32_t ntiles, const uint32_t* __restrict__ tile_offset,
@@ -682,7 +682,7 @@ __device__ __forceinline__ void stage_field_vec(const uint4* __restrict__ in4, u
     }
 
 template <int ITEMS, int RM>
-__global__ void __launch_bounds__(SORT_THREADS)
+__global__ void __launch_bounds__(SORT_THREADS, 2)
     k4_bucket_aos(const uint32_t* __restrict__ keys_in, uint32_t* __restrict__ keys_out, uint32_t* __restrict__ aos_out,
                   uint64_t n, int shift, uint32_t ntiles, const uint32_t* __restrict__ tile_offset,
                   const unsigned long long* __restrict__ digit_base, const __grid_constant__ AosArgs args)
