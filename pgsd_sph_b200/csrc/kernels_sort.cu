@@ -622,6 +622,7 @@ constexpr size_t ROWS_SMEM = (size_t)(ROWS_TILE + ROWS_STAGE_WORDS + SORT_WARPS 
 // particle side by side, RW words).  The whole tile is staged in shared memory in sorted order and
 // leaves as one contiguous run per bucket (hundreds of bytes instead of one short run per field);
 // the gather that follows reads 2 sectors per particle instead of one per field.
+constexpr int AOS_MAX_ROW_WORDS = 40;
 struct AosField
     {
     const uint32_t* in; // n rows of `words` words; NULL: the row's original index
@@ -636,51 +637,6 @@ struct AosArgs
     uint32_t row_words; // RW
     };
 
-// One field of a full, 16-byte aligned tile -> interleaved rows in shared memory.  WC > 0: W is the
-// compile-time constant WC (divisions fold into multiplies); WC == 0: runtime W.
-template <int TILE, int WC>
-__device__ __forceinline__ void stage_field_vec(const uint4* __restrict__ in4, uint32_t W_rt, uint32_t RW, uint32_t off,
-                                                const uint16_t* __restrict__ spos, uint32_t* __restrict__ stage)
-    {
-    const uint32_t W = WC > 0 ? (uint32_t)WC : W_rt;
-    const int tid = threadIdx.x;
-    const uint32_t nvec = (uint32_t)TILE * W / 4;
-    for (uint32_t v0 = 0; v0 < nvec; v0 += 4 * SORT_THREADS)
-        {
-        uint4 v[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++)
-            {
-            const uint32_t vq = v0 + tid + k * SORT_THREADS;
-            if (vq < nvec)
-                v[k] = ldg_stream_v4(in4 + vq);
-            }
-#pragma unroll
-        for (int k = 0; k < 4; k++)
-            {
-            const uint32_t vq = v0 + tid + k * SORT_THREADS;
-            if (vq < nvec)
-                {
-                const uint32_t words[4] = { v[k].x, v[k].y, v[k].z, v[k].w };
-                uint32_t e = (vq * 4) / W, c = vq * 4 - e * W;
-                uint32_t base = (uint32_t)spos[e] * RW + off;
-#pragma unroll
-                for (int u = 0; u < 4; u++)
-                    {
-                    stage[base + c] = words[u];
-                    if (++c == W)
-                        {
-                        c = 0;
-                        e++;
-                        if (u < 3)
-                            base = (uint32_t)spos[e] * RW + off;
-                        }
-                    }
-                }
-            }
-        }
-    }
-
 template <int ITEMS, int RM>
 __global__ void __launch_bounds__(SORT_THREADS, 2)
     k4_bucket_aos(const uint32_t* __restrict__ keys_in, uint32_t* __restrict__ keys_out, uint32_t* __restrict__ aos_out,
@@ -690,13 +646,14 @@ __global__ void __launch_bounds__(SORT_THREADS, 2)
     constexpr int TILE = SORT_THREADS * ITEMS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* skeys = reinterpret_cast<uint32_t*>(smem_raw);          // TILE : keys in tile-sorted order
-    uint16_t* spos = reinterpret_cast<uint16_t*>(skeys + TILE);       // TILE : row -> sorted position
+    uint16_t* sinv = reinterpret_cast<uint16_t*>(skeys + TILE);       // TILE : sorted position -> tile row
     TileRankSmem sm;
-    sm.whist = reinterpret_cast<uint32_t*>(spos + TILE);
+    sm.whist = reinterpret_cast<uint32_t*>(sinv + TILE);
     sm.dstart = sm.whist + SORT_WARPS * RADIX;
     sm.gdelta = reinterpret_cast<unsigned long long*>(sm.dstart + RADIX);
-    uint32_t* stage = reinterpret_cast<uint32_t*>(sm.gdelta + RADIX); // TILE * RW
+    uint32_t* raw = reinterpret_cast<uint32_t*>(sm.gdelta + RADIX);   // TILE * (words of the real fields), field-major
     __shared__ uint32_t wtot[8];
+    __shared__ uint32_t col[AOS_MAX_ROW_WORDS]; // column c of the interleaved row: (raw base << 8) | W; W = 0: original index
     sm.wtot = wtot;
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -705,6 +662,36 @@ __global__ void __launch_bounds__(SORT_THREADS, 2)
     const uint32_t tile_n = (uint32_t)((n - tile_base) < (uint64_t)TILE ? (n - tile_base) : TILE);
     const uint32_t wbase = (uint32_t)w * (32 * ITEMS);
 
+    // (1) the tile of every field starts its way global -> shared now (cp.async, no registers held);
+    //     ranking the keys below overlaps with the DRAM latency of the payload
+    uint32_t fbase = 0; // word offset of the field's tile copy in raw[]
+    for (int fi = 0; fi < args.nfields; fi++)
+        {
+        const AosField f = args.f[fi];
+        const uint32_t W = f.words;
+        if (tid < (int)W)
+            col[f.off + tid] = f.in ? (((fbase + (uint32_t)tid) << 8) | W) : 0u;
+        if (f.in == nullptr)
+            continue;
+        const uint32_t* in = f.in + tile_base * W;
+        const uint32_t total = tile_n * W;
+        const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(raw + fbase);
+        if (tile_n == TILE && (reinterpret_cast<uintptr_t>(in) & 15u) == 0)
+            {
+            const uint32_t nvec = total / 4;
+            for (uint32_t vq = tid; vq < nvec; vq += SORT_THREADS)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + vq * 16), "l"(in + vq * 4) : "memory");
+            }
+        else
+            {
+            for (uint32_t q = tid; q < total; q += SORT_THREADS)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sbase + q * 4), "l"(in + q) : "memory");
+            }
+        fbase += (uint32_t)TILE * W;
+        }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+
+    // (2) rank the keys
     uint32_t key[ITEMS], pos[ITEMS];
 #pragma unroll
     for (int k = 0; k < ITEMS; k++)
@@ -720,62 +707,14 @@ __global__ void __launch_bounds__(SORT_THREADS, 2)
         if (e < tile_n)
             {
             skeys[pos[k]] = key[k];
-            spos[e] = (uint16_t)pos[k];
+            sinv[pos[k]] = (uint16_t)e;
             }
         }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
-    // fields -> interleaved rows in shared memory, in sorted order.  Global loads are flat and
-    // coalesced (16-byte vectors on full, aligned tiles) and issued in batches before their stores.
-    for (int fi = 0; fi < args.nfields; fi++)
-        {
-        const AosField f = args.f[fi];
-        const uint32_t W = f.words;
-        if (f.in == nullptr)
-            {
-            for (uint32_t e = tid; e < tile_n; e += SORT_THREADS)
-                stage[(uint32_t)spos[e] * RW + f.off] = (uint32_t)(tile_base + e);
-            continue;
-            }
-        const uint32_t total = tile_n * W;
-        const uint32_t* in = f.in + tile_base * W;
-        if (tile_n == TILE && (reinterpret_cast<uintptr_t>(in) & 15u) == 0)
-            {
-            const uint4* in4 = reinterpret_cast<const uint4*>(in);
-            switch (W)
-                {
-                case 1: stage_field_vec<TILE, 1>(in4, W, RW, f.off, spos, stage); break;
-                case 2: stage_field_vec<TILE, 2>(in4, W, RW, f.off, spos, stage); break;
-                case 3: stage_field_vec<TILE, 3>(in4, W, RW, f.off, spos, stage); break;
-                case 4: stage_field_vec<TILE, 4>(in4, W, RW, f.off, spos, stage); break;
-                default: stage_field_vec<TILE, 0>(in4, W, RW, f.off, spos, stage); break;
-                }
-            }
-        else
-            {
-            for (uint32_t q0 = 0; q0 < total; q0 += 8 * SORT_THREADS)
-                {
-                uint32_t v[8];
-#pragma unroll
-                for (int k = 0; k < 8; k++)
-                    {
-                    const uint32_t q = q0 + tid + k * SORT_THREADS;
-                    v[k] = q < total ? ld_stream_u32(in + q) : 0u;
-                    }
-#pragma unroll
-                for (int k = 0; k < 8; k++)
-                    {
-                    const uint32_t q = q0 + tid + k * SORT_THREADS;
-                    if (q < total)
-                        {
-                        const uint32_t e = q / W, c = q - e * W;
-                        stage[(uint32_t)spos[e] * RW + f.off + c] = v[k];
-                        }
-                    }
-                }
-            }
-        }
-    __syncthreads();
-    // out: keys as digit runs; rows as one contiguous run of RW-word records per digit
+
+    // (3) out: keys as digit runs; rows as one contiguous run of RW-word records per digit, read from
+    //     the raw field tiles through the sorted-position -> row map
     if (keys_out)
         {
 #pragma unroll
@@ -791,17 +730,21 @@ __global__ void __launch_bounds__(SORT_THREADS, 2)
         }
     if ((RW & 1u) == 0)
         {
-        // rows are 8-byte multiples: move them as 64-bit pieces (half the instructions per byte)
+        // rows are 8-byte multiples: one 64-bit store per two columns
         const uint32_t R2 = RW / 2;
         const uint32_t total2 = tile_n * R2;
-        const uint2* stage2 = reinterpret_cast<const uint2*>(stage);
         uint2* out2 = reinterpret_cast<uint2*>(aos_out);
         uint32_t j = tid / R2, c = tid - j * R2;
         const uint32_t dj = SORT_THREADS / R2, dc = SORT_THREADS - dj * R2;
         for (uint32_t q = tid; q < total2; q += SORT_THREADS)
             {
             const unsigned long long g = sm.gdelta[(skeys[j] >> shift) & 255u] + j;
-            out2[g * R2 + c] = stage2[q];
+            const uint32_t e = sinv[j];
+            const uint32_t c0 = col[2 * c], c1 = col[2 * c + 1];
+            uint2 v;
+            v.x = (c0 & 255u) ? raw[(c0 >> 8) + e * (c0 & 255u)] : (uint32_t)(tile_base + e);
+            v.y = (c1 & 255u) ? raw[(c1 >> 8) + e * (c1 & 255u)] : (uint32_t)(tile_base + e);
+            out2[g * R2 + c] = v;
             j += dj;
             c += dc;
             if (c >= R2)
@@ -819,7 +762,9 @@ __global__ void __launch_bounds__(SORT_THREADS, 2)
         for (uint32_t q = tid; q < total_out; q += SORT_THREADS)
             {
             const unsigned long long g = sm.gdelta[(skeys[j] >> shift) & 255u] + j;
-            aos_out[g * RW + c] = stage[q];
+            const uint32_t e = sinv[j];
+            const uint32_t cc = col[c];
+            aos_out[g * RW + c] = (cc & 255u) ? raw[(cc >> 8) + e * (cc & 255u)] : (uint32_t)(tile_base + e);
             j += dj;
             c += dc;
             if (c >= RW)
@@ -841,7 +786,6 @@ template <int ITEMS> constexpr size_t aos_smem_fixed()
 // A warp owns 4 chunks of 32 consecutive output rows.  The source rows go global -> shared with
 // cp.async (no registers held while ~40 random 4/8-byte reads per lane are in flight), then every
 // field is written out fully coalesced from the staged rows.
-constexpr int AOS_MAX_ROW_WORDS = 40;
 constexpr int GA_THREADS = 128;
 constexpr int GA_CHUNKS = 4;
 constexpr int GA_ROWS_PER_CTA = (GA_THREADS / 32) * 32 * GA_CHUNKS;
