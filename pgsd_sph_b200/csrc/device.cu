@@ -145,7 +145,8 @@ Ctx g;
 bool write_piece(int fd, const char* p, uint64_t off, uint64_t len, uint64_t* left_out)
     {
     uint64_t left = len;
-    if (g.file_mmap && len > 0)
+    // small pieces stay on pwrite: they share pages with other writers' pieces and gain nothing
+    if (g.file_mmap && len >= (1u << 20))
         {
         static const uint64_t page = (uint64_t)sysconf(_SC_PAGESIZE);
         struct stat st;
