@@ -20,6 +20,8 @@ def main():
     ap.add_argument("--pack-particles", type=int, default=64 * 1024 * 1024)
     ap.add_argument("--sort-particles", type=int, default=16 * 1024 * 1024)
     ap.add_argument("--iters", type=int, default=3)
+    ap.add_argument("--frame", action="store_true",
+                    help="also write one whole 6-chunk frame through pgsd.fl (the real one-launch-per-frame K1)")
     a = ap.parse_args()
     lib = _lib.load()
     _lib.check(lib.pgsd_b200_device_init(0), "device_init")
@@ -39,6 +41,26 @@ def main():
     for d in cols_d + [out]:
         d.free()
     del cols_h, got
+
+    if a.frame:
+        import tempfile
+        from pgsd_sph_b200 import fl
+        d = "/dev/shm" if os.access("/dev/shm", os.W_OK) else tempfile.gettempdir()
+        path = os.path.join(d, "pgsd_profile_frame.gsd")
+        cols_h = [rng.random(n, dtype=np.float32) for _ in range(8)] + [rng.integers(0, 3, n, dtype=np.uint32),
+                                                                       rng.permutation(n).astype(np.uint32)]
+        cols_d = [DeviceArray.from_numpy(c) for c in cols_h]
+        chunks = (("particles/position", (0, 1, 2)), ("particles/velocity", (3, 4, 5)), ("particles/typeid", (8,)),
+                  ("particles/density", (6,)), ("particles/pressure", (7,)), ("log/particles/id", (9,)))
+        with fl.open(path, 'w', 'pgsd-b200', 'hoomd', [1, 4]) as f:
+            prep = f.prepare_frame_soa([(nm, [cols_d[j] for j in idx], None, None, True) for nm, idx in chunks])
+            for _ in range(2):
+                f.write_frame_soa(prep)
+                f.end_frame()
+        os.unlink(path)
+        for d_ in cols_d:
+            d_.free()
+        del cols_h
 
     # K4 + K5: 40 B/particle frame
     n = a.sort_particles
