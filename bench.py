@@ -227,7 +227,7 @@ def run_read_leg(lib, dist, args, peaks, windows):
     from pgsd_sph_b200.devmem import DeviceArray
     n = args.read_particles
     path = os.path.join(bench_dir(), f"read_r{dist.rank}.gsd")
-    nframes = 3
+    nframes = 7   # frame 0 + 6 frames read round-robin (sequential access: the reader prefetches i+1)
     t0 = time.perf_counter()
     frames = []
     with fl.open(path, 'w', 'pgsd-b200', 'hoomd', [1, 4]) as f:

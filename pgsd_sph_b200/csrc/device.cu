@@ -839,6 +839,8 @@ int dev_read_file_to_device(int fd, void* dev_dst, uint64_t bytes, uint64_t file
         return rc;
     if (bytes == 0)
         return 0;
+    static std::mutex read_mu; // the reader contexts are shared: one read at a time (a prefetch thread may call us)
+    std::lock_guard<std::mutex> read_lk(read_mu);
     rc = readers_init();
     if (rc != 0)
         return rc;

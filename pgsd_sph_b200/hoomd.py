@@ -282,9 +282,12 @@ class HOOMDTrajectory(object):
         file (:py:class:`pgsd_sph_b200.fl.PGSDFile`): File to access.
         reorder (None or 'id'): return frames in particle-ID order (GPU radix sort + gather).
         device (bool): keep per-particle arrays on the GPU.
+        prefetch (bool or None): read frame i+1's per-particle chunks into device memory on a helper
+            thread while frame i is processed (default: on for device / reorder reads of
+            read-only single-rank files).
     """
 
-    def __init__(self, file, reorder=None, device=False):
+    def __init__(self, file, reorder=None, device=False, prefetch=None):
         if file.mode == 'ab':
             raise ValueError('Append mode not yet supported')
         if reorder not in (None, 'id'):
@@ -296,6 +299,16 @@ class HOOMDTrajectory(object):
         # reorder='id': per-particle chunks go file -> pinned -> HBM directly (no host array in between),
         # are sorted + gathered there, and come back with one D2H copy per field
         self._read_device = self._device or reorder == 'id'
+        # sequential access (for frame in traj / traj[i], traj[i+1], ...): while frame i is sorted and
+        # copied back, a helper thread already pulls the per-particle chunks of frame i+1 from the file
+        # into device memory through a second read-only handle.  Single-rank read-only files only
+        # (every library call on a multi-rank communicator is collective).
+        if prefetch is None:
+            prefetch = self._read_device
+        self._prefetch_on = bool(prefetch) and self._read_device and file.mode == 'r' \
+            and _lib.load().pgsd_b200_comm_size() == 1
+        self._pf = None       # (frame index, thread, {chunk name: DeviceArray}, [error])
+        self._pf_file = None
         logger.info('opening HOOMDTrajectory: ' + str(self.file))
         if self.file.schema != 'hoomd':
             raise RuntimeError('PGSD file is not a hoomd schema file: ' + str(self.file))
@@ -370,6 +383,10 @@ class HOOMDTrajectory(object):
 
     def close(self):
         """Close the file."""
+        self._drop_prefetch()
+        if self._pf_file is not None:
+            self._pf_file.close()
+            self._pf_file = None
         self.file.close()
         self._initial_frame = None
 
@@ -381,6 +398,67 @@ class HOOMDTrajectory(object):
     def read_frame(self, idx):
         warnings.warn("Deprecated, trajectory[idx]", DeprecationWarning)
         return self._read_frame(idx)
+
+    _BIG_PREFIXES = ('particles/', 'log/particles/')
+
+    def _start_prefetch(self, idx):
+        if not self._prefetch_on or idx >= len(self) or idx < 0:
+            return
+        if self._pf is not None and self._pf[0] == idx:
+            return
+        self._drop_prefetch()
+        import threading
+        if self._pf_file is None:
+            self._pf_file = fl.open(self.file.name, 'r')
+        names = [n for n in self._per_particle_names()]
+        out, err = {}, []
+
+        def work():
+            try:
+                for n in names:
+                    if self._pf_file.chunk_exists(idx, n):
+                        out[n] = self._pf_file.read_chunk(idx, n, device=True)
+            except Exception as e:  # surfaced on the consuming side as a plain synchronous read
+                err.append(e)
+
+        t = threading.Thread(target=work, daemon=True)
+        t.start()
+        self._pf = (idx, t, out, err)
+
+    def _drop_prefetch(self):
+        if self._pf is not None:
+            self._pf[1].join()
+            for v in self._pf[2].values():
+                v.free()
+            self._pf = None
+
+    def _take_prefetched(self, idx):
+        """Chunks of frame idx read ahead of time ({} if none)."""
+        if self._pf is None:
+            return {}
+        if self._pf[0] != idx:
+            self._drop_prefetch()
+            return {}
+        _, t, out, err = self._pf
+        t.join()
+        self._pf = None
+        if err:
+            for v in out.values():
+                v.free()
+            return {}
+        return out
+
+    def _per_particle_names(self):
+        names = ['particles/' + n for n in ParticleData._default_value if n not in ('N', 'types', 'type_shapes')]
+        names += [n for n in self.file.find_matching_chunk_names('log/particles/', False)]
+        return names
+
+    def _read_big(self, idx, name, ahead):
+        """A per-particle chunk of frame idx: the prefetched device copy if there is one."""
+        v = ahead.pop(name, None)
+        if v is not None:
+            return v.reshape(v.shape[0]) if len(v.shape) == 2 and v.shape[1] == 1 else v
+        return self.file.read_chunk(frame=idx, name=name, offset=0, r_all=False, device=self._read_device)
 
     def _chunk_or_fallback(self, idx, name, initial, default):
         if self.file.chunk_exists(frame=idx, name=name, write_all=False):
@@ -404,6 +482,7 @@ class HOOMDTrajectory(object):
         # frame 0 is the fallback source for chunks missing in later frames
         if self._initial_frame is None and idx != 0:
             self._read_frame(0)
+        ahead = self._take_prefetched(idx)
         snap = Frame()
         cfg = snap.configuration
         v, hit = self._chunk_or_fallback(idx, 'configuration/step', lambda f0: f0.configuration.step,
@@ -439,9 +518,11 @@ class HOOMDTrajectory(object):
                 if name in ('N', 'types', 'type_shapes'):
                     continue
                 if self.file.chunk_exists(frame=idx, name=path + '/' + name, write_all=False):
-                    dev = self._read_device and path == 'particles'
-                    container.__dict__[name] = self.file.read_chunk(frame=idx, name=path + '/' + name,
-                                                                    offset=0, r_all=False, device=dev)
+                    if path == 'particles':
+                        container.__dict__[name] = self._read_big(idx, path + '/' + name, ahead)
+                    else:
+                        container.__dict__[name] = self.file.read_chunk(frame=idx, name=path + '/' + name,
+                                                                        offset=0, r_all=False)
                     if path == 'particles':
                         read_here[name] = True
                 else:
@@ -460,13 +541,18 @@ class HOOMDTrajectory(object):
 
         for log in self.file.find_matching_chunk_names('log/', False):
             if self.file.chunk_exists(frame=idx, name=log, write_all=False):
-                dev = self._read_device and log.startswith('log/particles/')
-                snap.log[log[4:]] = self.file.read_chunk(frame=idx, name=log, offset=0, r_all=False, device=dev)
+                if log.startswith('log/particles/'):
+                    snap.log[log[4:]] = self._read_big(idx, log, ahead)
+                else:
+                    snap.log[log[4:]] = self.file.read_chunk(frame=idx, name=log, offset=0, r_all=False)
             elif self._initial_frame is not None and log[4:] in self._initial_frame.log:
                 snap.log[log[4:]] = self._initial_frame.log[log[4:]]
 
+        for v in ahead.values():  # prefetched but unused (should not happen)
+            v.free()
         if self._initial_frame is None and idx == 0:
             self._initial_frame = snap
+        self._start_prefetch(idx + 1)
         if self._reorder == 'id':
             return self._reordered(snap)
         return snap
@@ -542,12 +628,12 @@ class HOOMDTrajectory(object):
         self.file.close()
 
 
-def open(name, mode='r', reorder=None, device=False):
-    """Open a hoomd schema PGSD file (ref: hoomd.py:943-989).  ``reorder`` / ``device``: see
-    :py:class:`HOOMDTrajectory`."""
+def open(name, mode='r', reorder=None, device=False, prefetch=None):
+    """Open a hoomd schema PGSD file (ref: hoomd.py:943-989).  ``reorder`` / ``device`` / ``prefetch``:
+    see :py:class:`HOOMDTrajectory`."""
     pgsdfileobj = fl.open(name=str(name), mode=mode, application='pgsd.hoomd ' + __version__,
                           schema='hoomd', schema_version=[1, 4])
-    return HOOMDTrajectory(pgsdfileobj, reorder=reorder, device=device)
+    return HOOMDTrajectory(pgsdfileobj, reorder=reorder, device=device, prefetch=prefetch)
 
 
 def read_log(name, scalar_only=False):
