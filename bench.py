@@ -434,7 +434,7 @@ def run_write_leg(lib, dist, args, peaks, windows):
                 "d2h_bytes_per_step": int(dist.sum(float(e2e["stats"].d2h_bytes))) // args.steps,
                 "path": "pinned host SoA columns -> pgsd_b200_write_chunks_soa (H2D, K1, D2H) -> pwrite -> file"},
         "roofline": {"bound": "hbm", "achieved": k1_bytes / k1_s / 1e9, "peak": peak, "unit": "GB/s",
-                     "frac": k1_bytes / k1_s / 1e9 / peak, "traffic": None, "peak_source": peaks["source"],
+                     "frac": k1_bytes / k1_s / 1e9 / peak, "traffic": k1_traffic(n), "peak_source": peaks["source"],
                      "kernel": "k1_pack_frame", "ms": k1_s * 1e3, "algorithmic_bytes": k1_bytes},
         "gpu_launches": int(dist.sum(float(dev["stats"].kernel_launches))),
         "split": {"device_k1_ms_per_frame": k1_s * 1e3,
@@ -444,6 +444,16 @@ def run_write_leg(lib, dist, args, peaks, windows):
                   "note": "wall = max(K1, D2H over PCIe, pwrite into the page cache); K1 is <1% of it"},
     }
     return out
+
+
+def k1_traffic(n):
+    """DRAM bytes of one K1 launch from the committed ncu capture (profiles/k1_traffic.json), scaled
+    to this launch's particle count; None if the capture is missing."""
+    p = os.path.join(REPO, "profiles", "k1_traffic.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    return int(d["traffic_bytes"] * (n / d["particles"]))
 
 
 def load_peaks():
