@@ -424,6 +424,14 @@ int dev_init(int device)
             set_last_error("device already initialised on another GPU");
             return -2;
             }
+        // The current device is per host thread and defaults to GPU 0: a caller's helper thread
+        // (e.g. the frame prefetcher of pgsd.hoomd) must land on this rank's GPU as well.
+        static thread_local bool bound = false;
+        if (!bound)
+            {
+            CUDA_TRY(cudaSetDevice(g.device), -1);
+            bound = true;
+            }
         return 0;
         }
     int n = 0;
@@ -1266,6 +1274,8 @@ int dev_free(void* p)
     {
     if (!p)
         return 0;
+    if (g.inited)
+        dev_init(-1); // binds this host thread to the rank's GPU
     // the block may be handed out again at once: everything queued on the caller's stream that
     // could still touch it must have finished (what cudaFree guarantees implicitly)
     CUDA_TRY(cudaStreamSynchronize(g.user), -1);
@@ -1316,6 +1326,8 @@ int dev_memcpy(void* dst, const void* src, uint64_t bytes, int kind)
     }
 int dev_synchronize()
     {
+    if (g.inited)
+        dev_init(-1); // binds this host thread to the rank's GPU
     if (!g.inited)
         return 0;
     CUDA_TRY(cudaDeviceSynchronize(), -1);
