@@ -531,12 +531,13 @@ class HOOMDTrajectory(object):
                         if initial.__dict__.get('_isdefault_' + name):
                             container.__dict__['_isdefault_' + name] = True
                     else:
+                        # the reference fills an N-row array with the default and marks it read-only
+                        # (hoomd.py:871-881) -- 76 B/particle of constants per frame 0; a zero-stride
+                        # broadcast view has the same shape, dtype, values and read-only flag for free
                         tmp = numpy.array([container._default_value[name]])
                         s = list(tmp.shape)
-                        s[0] = container.N
-                        container.__dict__[name] = numpy.empty(shape=s, dtype=tmp.dtype)
-                        container.__dict__[name][:] = tmp
-                        container.__dict__[name].flags.writeable = False
+                        s[0] = int(container.N)
+                        container.__dict__[name] = numpy.broadcast_to(tmp[0], s)
                         container.__dict__['_isdefault_' + name] = True
 
         for log in self.file.find_matching_chunk_names('log/', False):
