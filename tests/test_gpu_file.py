@@ -168,3 +168,17 @@ def test_roundtrip_1M_device_write_then_reordered_read(tmp_path):
         assert got.particles.velocity.tobytes() == fr["particles/velocity"][o].tobytes()
         assert got.particles.density.tobytes() == fr["particles/density"][o].tobytes()
         assert got.particles.typeid.tobytes() == fr["particles/typeid"][o].tobytes()
+
+
+def test_vtu_columns_on_device_match_numpy(golden):
+    """K6 = K1's strided cast path: (N,3) float32 on the device -> three contiguous float64 columns."""
+    from pgsd_sph_b200 import vtu
+    with hoomd.open(os.path.join(golden, "hoomd_p2.gsd"), 'r', reorder='id', device=True) as t:
+        fr = t[2]
+        x, y, z, pd = vtu.point_arrays(fr)
+        pos = fr.particles.position.to_numpy()
+        vel = fr.particles.velocity.to_numpy()
+        for j, c in enumerate((x, y, z)):
+            assert c.to_numpy().tobytes() == np.ascontiguousarray(pos[:, j], dtype=np.float64).tobytes()
+        assert pd['velocity'][1].to_numpy().tobytes() == np.ascontiguousarray(vel[:, 1], dtype=np.float64).tobytes()
+        assert pd['density'].to_numpy().tobytes() == fr.particles.density.to_numpy().astype(np.float64).tobytes()

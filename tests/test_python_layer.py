@@ -153,3 +153,24 @@ def test_hoomd_append_defaults_and_frame0_fallback(tmp_path):
         assert c.particles.position.shape == (n + 1, 3) and (c.particles.position == 0).all()   # default, N changed
         assert (c.particles.typeid == 0).all()
         assert a.log['value/e'][0] == np.float32(1.5) and b.log['value/e'][0] == np.float32(1.5)
+
+
+def test_vtu_point_arrays_and_file(golden, tmp_path):
+    """pgsd2vtu input preparation == the manual's numpy.ascontiguousarray(col, float64) (pgsd.tex:1249-1259);
+    the .vtu container itself is this repository's own format choice (parity unpinned: pyevtk absent)."""
+    from pgsd_sph_b200 import vtu
+    with hoomd.open(os.path.join(golden, "hoomd_p2.gsd"), 'r') as t:
+        fr = t[1]
+        x, y, z, pd = vtu.point_arrays(fr)
+        assert x.dtype == np.float64 and x.flags.c_contiguous
+        assert x.tobytes() == np.ascontiguousarray(fr.particles.position[:, 0], dtype=np.float64).tobytes()
+        assert pd['velocity'][2].tobytes() == np.ascontiguousarray(fr.particles.velocity[:, 2], dtype=np.float64).tobytes()
+        assert pd['slength'].shape == (int(fr.particles.N),) and (pd['slength'] == 1).all()  # schema default (hoomd.py:178)
+        name = vtu.write_vtu(str(tmp_path / "f_00001"), x, y, z, pd)
+    raw = open(name, 'rb').read()
+    head, tail = raw.split(b'<AppendedData encoding="raw">\n_', 1)
+    assert b'NumberOfPoints="512"' in head and b'Name="velocity" NumberOfComponents="3"' in head
+    n = 512
+    first = int.from_bytes(tail[:8], 'little')
+    assert first == n * 3 * 8
+    assert np.frombuffer(tail[8:8 + first], dtype=np.float64).reshape(n, 3)[:, 1].tobytes() == y.tobytes()
