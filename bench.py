@@ -456,6 +456,51 @@ def k1_traffic(n):
     return int(d["traffic_bytes"] * (n / d["particles"]))
 
 
+def run_benchmark_write_leg(lib, dist, args):
+    """The reference's own published benchmark (scripts/benchmark-write.cc:30-45,85-160; CHANGELOG.md:172-194):
+    17 keys x 100 frames x 1 Mi float64 per key, rows split over the ranks, every key written with
+    all=true at the caller-computed offset; throughput = MiB written in the SECOND 50 frames / their time.
+    Here the keys are device-resident arrays handed to pgsd_write_chunk as device pointers."""
+    from pgsd_sph_b200 import fl
+    from pgsd_sph_b200.devmem import DeviceArray
+    nkeys, nframes, n_total = 17, 100, 1024 * 1024
+    rows, start = rank_rows(n_total, dist.world, dist.rank)
+    n = rows[dist.rank]
+    rng = np.random.default_rng(11 + dist.rank)
+    keys = [DeviceArray.from_numpy(rng.standard_normal(n)) for _ in range(nkeys)]
+    names = ["key%d" % k for k in range(nkeys)]
+    path = os.path.join(bench_dir(), "benchmark_write.gsd")
+    dist.barrier()
+    f = fl.open(path, 'w', 'pgsd-b200', 'benchmark', [1, 0])
+    t1 = None
+    for i in range(nframes):
+        if i == nframes // 2:
+            f.flush()
+            lib.pgsd_b200_synchronize()
+            dist.barrier()
+            t1 = time.perf_counter()
+        for nm, a in zip(names, keys):
+            f.write_chunk(nm, a, offset=rows, rank=dist.rank)
+        f.end_frame()
+    f.flush()
+    lib.pgsd_b200_synchronize()
+    t2 = time.perf_counter() - t1
+    dist.barrier()
+    t2 = dist.max(t2)
+    f.close()
+    dist.barrier()
+    if dist.rank == 0:
+        os.unlink(path)
+    for a in keys:
+        a.free()
+    mib = (nframes - nframes // 2) * nkeys * n_total * 8 / 1048576.0
+    return {"metric": "benchmark_write_MiBps", "value": mib / t2, "unit": "MiB/s", "seconds": t2,
+            "workload": "17 keys x 100 frames x 1 Mi float64 (14.26 GB), second 50 frames timed, as benchmark-write.cc",
+            "vs_baseline": mib / t2 / 167.0,
+            "vs_baseline_note": "published 167.0 MiB/s at 1 rank on NVMe (CHANGELOG.md:186); this run writes to "
+                                "tmpfs, so the ratio mixes implementation and storage"}
+
+
 def load_peaks():
     p = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -584,6 +629,7 @@ def main():
         from pgsd_sph_b200 import comm
         comm.init_nccl(dist.rank, dist.world, dist.bcast_bytes, dist.local)
     wr = run_write_leg(lib, dist, args, peaks, windows)
+    bw = run_benchmark_write_leg(lib, dist, args)
     sampler.stop()
 
     line = None
@@ -594,7 +640,7 @@ def main():
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(common_cfg, comm=lib.pgsd_b200_comm_kind().decode(), parallelism=f"rows/{dist.world}"),
             "e2e": wr["e2e"], "roofline": wr["roofline"], "gpu_launches": wr["gpu_launches"] + rd["gpu_launches"],
-            "split": wr["split"], "read_reorder": rd, "clocks": sampler.summary(windows),
+            "split": wr["split"], "read_reorder": rd, "benchmark_write": bw, "clocks": sampler.summary(windows),
             "vs_baseline_note": "BASELINE.md's only published number (0.175 GB/s benchmark-write, f64 keys, NVMe) is "
                                 "for another workload and storage; not used",
         }
