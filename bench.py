@@ -534,6 +534,26 @@ def cpu_write_reference(n, frames, nranks, warm=1):
     return {"s_per_frame": float(np.mean(t)), "GBps": BPP * n / float(np.mean(t)) / 1e9, "frames": len(t)}
 
 
+def cpu_benchmark_write_reference(nranks):
+    """The reference's OWN benchmark binary (scripts/benchmark-write.cc compiled unmodified against the
+    MPI shim): 17 keys x 100 frames x 1 Mi float64, prints "MB/s:" (MiB/s of the second 50 frames)."""
+    exe = os.path.join(REPO, "oracle", "_ref", "benchmark-write")
+    if not os.path.exists(exe):
+        return None
+    d = bench_dir()
+    r = subprocess.run([exe], cwd=d, env=dict(os.environ, PGSD_SHIM_NP=str(nranks)), capture_output=True, text=True)
+    out = os.path.join(d, "test%d.gsd" % nranks)
+    if os.path.exists(out):
+        os.unlink(out)
+    for line in r.stdout.splitlines():
+        if line.startswith("MB/s:"):
+            return {"metric": "benchmark_write_MiBps", "value": float(line.split()[1]), "unit": "MiB/s", "ranks": nranks,
+                    "workload": "17 keys x 100 frames x 1 Mi float64, unmodified benchmark-write.cc + pgsd.c + MPI shim",
+                    "vs_baseline": float(line.split()[1]) / 167.0}
+    log("benchmark-write failed:", r.stderr[-300:])
+    return None
+
+
 def cpu_read_reference(n, steps, warm=1):
     """Oracle port of the reference reader (pypgsd + hoomd decode) + numpy stable argsort + gather."""
     from oracle import reader_oracle, reorder_oracle
@@ -589,6 +609,7 @@ def main():
         w = cpu_write_reference(n_w, args.steps, nr, warm=max(1, args.warmup))
         n_r = min(args.read_particles, 2 * 1024 * 1024)
         r = cpu_read_reference(n_r, min(args.steps, 4), warm=1)
+        bw = cpu_benchmark_write_reference(min(ncores, 8))
         if w is None:
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_driver is not built"}))
             return 0
@@ -601,6 +622,7 @@ def main():
                              "sample": f"{w['frames']} frames of {n_w} particles, unmodified reference pgsd.c + MPI shim, "
                                        f"{nr} ranks (processes)"},
             "e2e": {"value": w["GBps"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "benchmark_write": bw,
             "read_reorder": {"metric": "id_reordered_read_Mparticles_per_s", "value": r["Mpps"], "unit": "Mparticles/s",
                              "e2e": {"value": r["Mpps"], "unit": "Mparticles/s", "h2d_bytes_per_step": 0,
                                      "d2h_bytes_per_step": 0},

@@ -18,4 +18,10 @@ gcc $CFLAGS -c "$HERE/shim/mpishim.c" -o "$OUT/mpishim.o"
 gcc $CFLAGS -c "$HERE/ref_driver.c" -o "$OUT/ref_driver.o"
 gcc -o "$OUT/ref_driver" "$OUT/ref_driver.o" "$OUT/pgsd_ref.o" "$OUT/mpishim.o" -lpthread -lm
 gcc -shared -o "$OUT/libpgsd_ref.so" "$OUT/pgsd_ref.o" "$OUT/mpishim.o" -lpthread
+# the reference's own C++ benchmark (published numbers: CHANGELOG.md:172-194), unmodified
+SCRIPTS="${PGSD_REFERENCE_ROOT:-/root/reference}/pgsd/scripts"
+if [ -f "$SCRIPTS/benchmark-write.cc" ]; then
+    g++ -O2 -w -I"$HERE/shim" -I"$REF" -o "$OUT/benchmark-write" "$SCRIPTS/benchmark-write.cc" \
+        "$OUT/pgsd_ref.o" "$OUT/mpishim.o" -lpthread
+fi
 echo "built $OUT/ref_driver and $OUT/libpgsd_ref.so from $REF/pgsd.c"
