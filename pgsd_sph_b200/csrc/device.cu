@@ -753,27 +753,34 @@ int dev_copy_to_host(void* host_dst, const void* dev_src, uint64_t bytes)
     return 0;
     }
 
-// file -> pinned -> device.  Large reads are split into 4 MiB pieces over 8 reader threads, each with
+// file -> pinned -> device.  Large reads are split into 1 MiB pieces over reader threads (8 by default), each with
 // its own pair of pinned buffers and copy stream: page-cache reads of one file scale with threads
 // (no exclusive inode lock on the read side) and overlap the H2D DMA of the previous pieces.
 namespace
     {
-constexpr uint64_t READ_PIECE = 4ull << 20;
-constexpr int READ_THREADS = 8;
+constexpr uint64_t READ_PIECE = 1ull << 20; // small pieces: the pipeline of a read fills in ~0.3 ms
+constexpr int READ_THREADS_MAX = 32;
+int g_read_threads = 8; // PGSD_B200_READER_THREADS (file -> pinned saturates near 35 GB/s from 6 threads up)
 struct Reader
     {
     char* buf[2] = { nullptr, nullptr };
     cudaEvent_t ev[2] = { nullptr, nullptr };
     cudaStream_t st = nullptr;
     };
-Reader g_readers[READ_THREADS];
+Reader g_readers[READ_THREADS_MAX];
 bool g_readers_ready = false;
 
 int readers_init()
     {
     if (g_readers_ready)
         return 0;
-    for (int i = 0; i < READ_THREADS; i++)
+    if (const char* e = getenv("PGSD_B200_READER_THREADS"))
+        {
+        int v = atoi(e);
+        if (v >= 1 && v <= READ_THREADS_MAX)
+            g_read_threads = v;
+        }
+    for (int i = 0; i < g_read_threads; i++)
         {
         Reader& r = g_readers[i];
         CUDA_TRY(cudaStreamCreateWithFlags(&r.st, cudaStreamNonBlocking), -1);
@@ -789,7 +796,7 @@ int readers_init()
 
 void readers_release()
     {
-    for (int i = 0; i < READ_THREADS; i++)
+    for (int i = 0; i < READ_THREADS_MAX; i++)
         {
         Reader& r = g_readers[i];
         for (int k = 0; k < 2; k++)
@@ -853,7 +860,7 @@ int dev_read_file_to_device(int fd, void* dev_dst, uint64_t bytes, uint64_t file
     if (rc != 0)
         return rc;
     const uint64_t npieces = (bytes + READ_PIECE - 1) / READ_PIECE;
-    const int T = npieces < (uint64_t)READ_THREADS ? (int)npieces : READ_THREADS;
+    const int T = npieces < (uint64_t)g_read_threads ? (int)npieces : g_read_threads;
     bool ok = true;
     if (T == 1)
         ok = reader_run(0, 1, fd, (char*)dev_dst, bytes, file_off);
