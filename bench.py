@@ -394,15 +394,37 @@ def run_write_leg(lib, dist, args, peaks, windows):
                     k1_ms.append(float(ms.value))
             f.end_frame()
 
+        # the trajectory file must fit the target: start a new file when it would pass the budget
+        # (only matters for very long runs; closing + reopening is inside the timed region then)
+        st_fs = os.statvfs(bench_dir())
+        budget = min(64 << 30, int(0.35 * st_fs.f_bavail * st_fs.f_frsize))
+        frames_per_file = max(1, budget // max(payload, 1))
+        in_file = 0
+
+        def roll():
+            nonlocal f, prep, in_file
+            if in_file < frames_per_file:
+                return
+            f.close()
+            dist.barrier()
+            f = fl.open(path, 'w', 'pgsd-b200', 'hoomd', [1, 4])
+            prep = f.prepare_frame_soa([(nm, [src[j] for j in idx], dt, rows, True) for nm, idx, dt in SOA_CHUNKS],
+                                       rank=dist.rank)
+            in_file = 0
+
         for i in range(args.warmup):
+            roll()
             step(i)
+            in_file += 1
         f.flush()
         lib.pgsd_b200_reset_stats()
         dist.barrier()
         lib.pgsd_b200_synchronize()
         w0 = time.perf_counter()
         for i in range(args.steps):
+            roll()
             step(args.warmup + i, timed=True)
+            in_file += 1
         f.flush()  # drains every queued D2H + pwrite of this rank
         lib.pgsd_b200_synchronize()
         dt = time.perf_counter() - w0
@@ -606,7 +628,11 @@ def main():
             return 0
         nr = min(ncores, 16)
         n_w = args.particles  # the full frame: a few seconds per step on the host cores
-        w = cpu_write_reference(n_w, args.steps, nr, warm=max(1, args.warmup))
+        st_fs = os.statvfs(bdir)
+        budget = min(64 << 30, int(0.35 * st_fs.f_bavail * st_fs.f_frsize)) - BPP * n_w  # minus the input blob
+        warm = max(1, min(args.warmup, 2))
+        steps_ref = max(1, min(args.steps, budget // (BPP * n_w) - warm))  # the file must fit the target
+        w = cpu_write_reference(n_w, steps_ref, nr, warm=warm)
         n_r = min(args.read_particles, 2 * 1024 * 1024)
         r = cpu_read_reference(n_r, min(args.steps, 4), warm=1)
         bw = cpu_benchmark_write_reference(min(ncores, 8))

@@ -23,6 +23,7 @@
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
+#include <sys/statvfs.h>
 #include <unistd.h>
 #include <vector>
 
@@ -151,6 +152,11 @@ bool write_piece(int fd, const char* p, uint64_t off, uint64_t len, uint64_t* le
         static const uint64_t page = (uint64_t)sysconf(_SC_PAGESIZE);
         struct stat st;
         bool sized = fstat(fd, &st) == 0 && S_ISREG(st.st_mode);
+        // a store into a mapping cannot report ENOSPC (it raises SIGBUS): leave nearly full file
+        // systems to pwrite, which returns the error
+        struct statvfs vfs;
+        if (sized && (fstatvfs(fd, &vfs) != 0 || (uint64_t)vfs.f_bavail * vfs.f_frsize < 4 * len + (256ull << 20)))
+            sized = false;
         if (sized && (uint64_t)st.st_size < off + len)
             sized = fallocate(fd, 0, (off_t)(off + len - 1), 1) == 0;
         if (sized)
