@@ -374,7 +374,7 @@ def run_write_leg(lib, dist, args, peaks, windows):
         p.array[...] = a
     h_cols = [p.array for p in pinned]
     payload = BPP * n_total
-    path = os.path.join(bench_dir(), "write.gsd")
+    path = os.path.join(bench_dir(), "write_A.gsd")
     result = {}
     for leg, src in (("device", d_cols), ("e2e", h_cols)):
         dist.barrier()
@@ -402,11 +402,15 @@ def run_write_leg(lib, dist, args, peaks, windows):
         in_file = 0
 
         def roll():
-            nonlocal f, prep, in_file
+            nonlocal f, prep, in_file, path
             if in_file < frames_per_file:
                 return
             f.close()
             dist.barrier()
+            old = path
+            path = old[:-5] + ("B.gsd" if old.endswith("A.gsd") else "A.gsd")
+            if dist.rank == 0:  # freeing tens of GB of page cache takes seconds: off the critical path
+                threading.Thread(target=os.unlink, args=(old,), daemon=False).start()
             f = fl.open(path, 'w', 'pgsd-b200', 'hoomd', [1, 4])
             prep = f.prepare_frame_soa([(nm, [src[j] for j in idx], dt, rows, True) for nm, idx, dt in SOA_CHUNKS],
                                        rank=dist.rank)
