@@ -133,7 +133,7 @@ struct pgsd_b200_field
     {
     const void* in;     /* n rows of row_bytes */
     void* out;          /* n rows of row_bytes, must not alias in */
-    uint32_t row_bytes; /* 1..64, e.g. 12 for an (N,3) float32 field */
+    uint32_t row_bytes; /* 1..1024, e.g. 12 for an (N,3) float32 field; multiples of 4 take the fast path */
     };
 
 /* K4: stable LSD radix sort of (key, original index) pairs on the device.
@@ -145,7 +145,9 @@ int pgsd_b200_sort_ids(uint64_t n, const uint32_t* keys_device, uint32_t* keys_s
 int pgsd_b200_gather(uint64_t n, const uint32_t* perm_device, int nfields,
                      const struct pgsd_b200_field* fields_device, void* cuda_stream);
 
-/* K4+K5 on device-resident data. */
+/* K4+K5 on device-resident data.  Frames of >= 1 Mi rows (PGSD_B200_BUCKET_MIN_ROWS) first get a
+   bucket pass: rows grouped by the top key bits into a workspace copy (n * (row bytes + 8) bytes of
+   device memory, cached between calls) so that the gather is L2-local. */
 int pgsd_b200_reorder_device(uint64_t n, const uint32_t* keys_device, uint32_t* keys_sorted_device,
                              uint32_t* perm_device, int nfields,
                              const struct pgsd_b200_field* fields_device, void* cuda_stream);

@@ -5,15 +5,23 @@
 // applied to the arrays pgsd.hoomd's frame decode returns in file (rank) order
 // (/root/reference/pgsd/pgsd/hoomd.py:724-902 never sorts; README.md:29).
 //
-// K4: 8-bit digits, least significant first.  One pre-pass builds the four global digit
-//     histograms so passes whose digit is constant are skipped (dense ids < 2^24 -> 3 passes).
-//     Each pass = tile histogram (shared-memory atomics) -> per-digit row scan -> scatter.
-//     The scatter ranks keys with warp-level __match_any_sync/popc against per-warp
-//     shared-memory digit counters, re-orders the tile in shared memory and writes
-//     digit runs out coalesced.  Everything is order preserving => the sort is stable.
-// K5: out[i] = in[perm[i]] for all fields in one launch; each warp owns 32 consecutive
-//     output rows and moves them word by word so that stores are fully coalesced and the
-//     words of one source row are fetched by adjacent lanes.
+// Pipeline of pgsd_b200_reorder_device (dev_reorder_rows below):
+//   census     k4_digit_census: the four byte histograms of the keys in one read; constant bytes
+//              are skipped, the highest varying bit selects the bucket digit.
+//   bucket     k4_bucket_aos: stable partition of WHOLE ROWS by the top 8 significant key bits into
+//              one interleaved copy -- afterwards the output rows of a bucket and their source rows
+//              occupy the same index range, so the final gather is local to a few MB (L2) instead of
+//              random over the frame.  (k4_bucket_rows: per-field copy for rows wider than 40 words;
+//              with a single varying key byte the bucket pass writes the final order directly.)
+//   pairs      LSD passes over (key, position in the bucketed copy), 8-bit digits: k4_tile_histogram
+//              (shared-memory atomics) -> k4_row_scan -> k4_digit_base -> k4_scatter.  Keys are ranked
+//              with warp ballots against per-warp shared-memory digit counters, the tile is re-ordered
+//              in (padded) shared memory and digit runs are written coalesced.  Order preserving =>
+//              every pass, and the whole sort, is stable.
+//   gather     k5_gather_aos: rows of the bucketed copy -> shared memory (cp.async, after a sequential
+//              L2 prefetch of the bucket slice) -> fields written back SoA, fully coalesced.
+// pgsd_b200_sort_ids = census + pairs on the caller's keys; pgsd_b200_gather = k5_gather, the plain
+// out[i] = in[perm[i]] for an arbitrary caller permutation.
 //
 // sm_100a only.  No CPU fallback: callers fail when CUDA is unavailable.
 #include "device_internal.h"
