@@ -1,23 +1,23 @@
+# cython: language_level=3, embedsignature=True
 """PGSD file layer API -- drop-in for the reference's ``pgsd.fl`` over libpgsd_b200.
 
-Same surface as the reference Cython module (/root/reference/pgsd/pgsd/fl.pyx:149-1052):
-:py:func:`open`, :py:class:`PGSDFile` with ``write_chunk / end_frame / flush / read_chunk /
-chunk_exists / find_matching_chunk_names / close``, the same properties, error mapping
-(fl.pyx:35-61) and context-manager / pickle behaviour.  What is new:
+Cython binding of the C ABI (include/pgsd.h, include/pgsd_b200.h), same surface as the reference's
+Cython module (/root/reference/pgsd/pgsd/fl.pyx:149-1052): :py:func:`open`, :py:class:`PGSDFile` with
+``write_chunk / end_frame / flush / read_chunk / chunk_exists / find_matching_chunk_names / close``,
+the same properties, error mapping (fl.pyx:35-61) and context-manager / pickle behaviour.  The C calls
+run ``with nogil`` like the reference's.  What is new:
 
 * ``data`` of :py:meth:`PGSDFile.write_chunk` may live on the GPU (anything exposing
   ``__cuda_array_interface__`` or ``__dlpack__``): contiguous arrays are handed to the C ABI as
   device pointers; strided ones are made contiguous by the K1 pack kernel on the device -- the
-  device-side ``numpy.ascontiguousarray`` of fl.pyx:571.
-* :py:meth:`PGSDFile.write_chunk_soa` packs + dtype-casts M separate component arrays into one
-  (N, M) chunk on the device (the ``ParticleData.validate`` contract, hoomd.py:206-270).
+  device-side ``numpy.ascontiguousarray`` of fl.pyx:571.  No PyTorch dependency.
+* :py:meth:`PGSDFile.write_chunk_soa` / :py:meth:`PGSDFile.write_frame_soa` pack + dtype-cast separate
+  component arrays into (N, M) chunks on the device (the ``ParticleData.validate`` contract,
+  hoomd.py:206-270), a whole frame with one kernel launch.
 * ``offset='auto'`` lets the library place this rank's rows at the exclusive prefix over ranks
   (K2) instead of the caller passing all ranks' row counts (fl.pyx:596-598).
 * :py:meth:`PGSDFile.read_chunk` can read straight into device memory (``device=True``).
-
-The calls release the GIL (ctypes foreign calls do, like the reference's ``with nogil`` blocks).
 """
-import ctypes as C
 import errno as _errno
 import logging
 import os
@@ -25,44 +25,61 @@ from pickle import PickleError
 
 import numpy
 
-from . import _lib
+from libc.errno cimport errno
+from libc.stdint cimport uint8_t, uint32_t, uint64_t, int64_t, uintptr_t
+from libc.stdlib cimport malloc, free
+from libc.string cimport memset
+from cpython.buffer cimport PyObject_GetBuffer, PyBuffer_Release, PyBUF_SIMPLE, PyBUF_WRITABLE
+
+cimport libpgsd
+
 from .devmem import DeviceArray, as_device_view, is_device_array
 
 logger = logging.getLogger('pgsd.fl')
 
 _NP_TO_PGSD = {
-    numpy.dtype(numpy.uint8): _lib.TYPE_UINT8, numpy.dtype(numpy.uint16): _lib.TYPE_UINT16,
-    numpy.dtype(numpy.uint32): _lib.TYPE_UINT32, numpy.dtype(numpy.uint64): _lib.TYPE_UINT64,
-    numpy.dtype(numpy.int8): _lib.TYPE_INT8, numpy.dtype(numpy.int16): _lib.TYPE_INT16,
-    numpy.dtype(numpy.int32): _lib.TYPE_INT32, numpy.dtype(numpy.int64): _lib.TYPE_INT64,
-    numpy.dtype(numpy.float32): _lib.TYPE_FLOAT, numpy.dtype(numpy.float64): _lib.TYPE_DOUBLE,
+    numpy.dtype(numpy.uint8): libpgsd.PGSD_TYPE_UINT8, numpy.dtype(numpy.uint16): libpgsd.PGSD_TYPE_UINT16,
+    numpy.dtype(numpy.uint32): libpgsd.PGSD_TYPE_UINT32, numpy.dtype(numpy.uint64): libpgsd.PGSD_TYPE_UINT64,
+    numpy.dtype(numpy.int8): libpgsd.PGSD_TYPE_INT8, numpy.dtype(numpy.int16): libpgsd.PGSD_TYPE_INT16,
+    numpy.dtype(numpy.int32): libpgsd.PGSD_TYPE_INT32, numpy.dtype(numpy.int64): libpgsd.PGSD_TYPE_INT64,
+    numpy.dtype(numpy.float32): libpgsd.PGSD_TYPE_FLOAT, numpy.dtype(numpy.float64): libpgsd.PGSD_TYPE_DOUBLE,
 }
+_NP_TO_PGSD = {k: int(v) for k, v in _NP_TO_PGSD.items()}
 _PGSD_TO_NP = {v: k for k, v in _NP_TO_PGSD.items()}
 
+cdef uint64_t _AUTO = 0xFFFFFFFFFFFFFFFFULL  # PGSD_B200_OFFSET_AUTO / N_global "auto"
 
-def _raise_on_error(retval, extra):
+
+cdef str _last_error():
+    cdef const char* m = libpgsd.pgsd_b200_last_error()
+    return m.decode('utf-8', 'replace') if m != NULL else ''
+
+
+cdef _raise_on_error(int retval, extra, int err=0):
     """Raise the appropriate error type (ref: fl.pyx:35-61)."""
-    if retval == _lib.ERROR_IO:
-        err = C.get_errno() or _errno.EIO
-        raise IOError(err, os.strerror(err), extra)
-    elif retval == _lib.ERROR_NOT_A_PGSD_FILE:
+    if retval == 0:
+        return
+    if retval == libpgsd.PGSD_ERROR_IO:
+        e = err or _errno.EIO
+        raise IOError(e, os.strerror(e), extra)
+    elif retval == libpgsd.PGSD_ERROR_NOT_A_PGSD_FILE:
         raise RuntimeError("Not a PGSD file: " + extra)
-    elif retval == _lib.ERROR_INVALID_PGSD_FILE_VERSION:
+    elif retval == libpgsd.PGSD_ERROR_INVALID_PGSD_FILE_VERSION:
         raise RuntimeError("Unsupported PGSD file version: " + extra)
-    elif retval == _lib.ERROR_FILE_CORRUPT:
+    elif retval == libpgsd.PGSD_ERROR_FILE_CORRUPT:
         raise RuntimeError("Corrupt PGSD file: " + extra)
-    elif retval == _lib.ERROR_MEMORY_ALLOCATION_FAILED:
+    elif retval == libpgsd.PGSD_ERROR_MEMORY_ALLOCATION_FAILED:
         raise MemoryError("Memory allocation failed: " + extra)
-    elif retval == _lib.ERROR_NAMELIST_FULL:
+    elif retval == libpgsd.PGSD_ERROR_NAMELIST_FULL:
         raise RuntimeError("PGSD namelist is full: " + extra)
-    elif retval == _lib.ERROR_FILE_MUST_BE_WRITABLE:
+    elif retval == libpgsd.PGSD_ERROR_FILE_MUST_BE_WRITABLE:
         raise RuntimeError("File must be writable: " + extra)
-    elif retval == _lib.ERROR_FILE_MUST_BE_READABLE:
+    elif retval == libpgsd.PGSD_ERROR_FILE_MUST_BE_READABLE:
         raise RuntimeError("File must be readable: " + extra)
-    elif retval == _lib.ERROR_INVALID_ARGUMENT:
-        raise RuntimeError("Invalid pgsd argument: " + extra + " " + _lib.last_error())
-    elif retval != 0:
-        raise RuntimeError("Unknown error: " + extra + " " + _lib.last_error())
+    elif retval == libpgsd.PGSD_ERROR_INVALID_ARGUMENT:
+        raise RuntimeError("Invalid pgsd argument: " + extra + " " + _last_error())
+    else:
+        raise RuntimeError("Unknown error: " + extra + " " + _last_error())
 
 
 def open(name, mode, application=None, schema=None, schema_version=None):
@@ -74,34 +91,66 @@ def open(name, mode, application=None, schema=None, schema_version=None):
     return PGSDFile(str(name), mode, application, schema, schema_version)
 
 
-class PGSDFile:
+cdef class _PreparedFrame:
+    """C descriptor table of a frame's SoA chunks (see PGSDFile.prepare_frame_soa)."""
+    cdef libpgsd.pgsd_b200_chunk_desc* descs
+    cdef libpgsd.pgsd_b200_column* cols
+    cdef int n
+    cdef object keep
+
+    def __cinit__(self):
+        self.descs = NULL
+        self.cols = NULL
+        self.n = 0
+
+    def __dealloc__(self):
+        if self.descs != NULL:
+            free(self.descs)
+        if self.cols != NULL:
+            free(self.cols)
+
+
+cdef class PGSDFile:
     """PGSD file access interface (ref: fl.pyx:231-380)."""
 
+    cdef libpgsd.pgsd_handle _handle   # caller-owned handle, embedded by value (ref: fl.pyx:284)
+    cdef bint _is_open
+    cdef str _mode
+    cdef str _name
+
     def __init__(self, name, mode, application, schema, schema_version):
-        self._lib = _lib.load()
-        self._handle = _lib.Handle()
+        cdef libpgsd.pgsd_open_flag c_flags
+        cdef int exclusive_create = 0
+        cdef int overwrite = 0
+        cdef int retval = 0
+        cdef int err = 0
+        cdef uint32_t version
+        cdef bytes bname, bapp, bschema
+        cdef const char* c_name
+        cdef const char* c_app
+        cdef const char* c_schema
         self._is_open = False
         self._mode = mode
-        exclusive_create = 0
-        overwrite = 0
         if mode == 'w':
-            c_flags = _lib.OPEN_READWRITE
+            c_flags = libpgsd.PGSD_OPEN_READWRITE
             overwrite = 1
         elif mode == 'r':
-            c_flags = _lib.OPEN_READONLY
+            c_flags = libpgsd.PGSD_OPEN_READONLY
         elif mode == 'r+':
-            c_flags = _lib.OPEN_READWRITE
+            c_flags = libpgsd.PGSD_OPEN_READWRITE
         elif mode == 'x':
-            c_flags = _lib.OPEN_READWRITE
+            c_flags = libpgsd.PGSD_OPEN_READWRITE
             overwrite = 1
             exclusive_create = 1
         elif mode == 'a':
-            c_flags = _lib.OPEN_READWRITE
+            c_flags = libpgsd.PGSD_OPEN_READWRITE
             if not os.path.exists(name):
                 overwrite = 1
         else:
             raise ValueError("Invalid mode: " + mode)
         self._name = name
+        bname = name.encode('utf-8')
+        c_name = bname
 
         if overwrite:
             if application is None:
@@ -112,18 +161,25 @@ class PGSDFile:
                 raise ValueError("Provide schema_version when creating a file")
             logger.info('overwriting file: ' + name + ' with mode: ' + mode + ', application: ' + application
                         + ', schema: ' + schema + ', and schema_version: ' + str(schema_version))
-            if exclusive_create and os.path.exists(name) and self._lib.pgsd_b200_comm_size() == 1:
+            if exclusive_create and os.path.exists(name) and libpgsd.pgsd_b200_comm_size() == 1:
                 raise FileExistsError(_errno.EEXIST, os.strerror(_errno.EEXIST), name)
-            version = self._lib.pgsd_make_version(int(schema_version[0]), int(schema_version[1]))
-            retval = self._lib.pgsd_create_and_open(C.byref(self._handle), name.encode('utf-8'),
-                                                    application.encode('utf-8'), schema.encode('utf-8'),
-                                                    version, c_flags, exclusive_create)
+            version = libpgsd.pgsd_make_version(int(schema_version[0]), int(schema_version[1]))
+            bapp = application.encode('utf-8')
+            bschema = schema.encode('utf-8')
+            c_app = bapp
+            c_schema = bschema
+            with nogil:
+                retval = libpgsd.pgsd_create_and_open(&self._handle, c_name, c_app, c_schema, version, c_flags,
+                                                      exclusive_create)
+                err = errno
         else:
             logger.info('opening file: ' + name + ' with mode: ' + mode)
             if not os.path.exists(name):
                 raise FileNotFoundError(_errno.ENOENT, os.strerror(_errno.ENOENT), name)
-            retval = self._lib.pgsd_open(C.byref(self._handle), name.encode('utf-8'), c_flags)
-        _raise_on_error(retval, name)
+            with nogil:
+                retval = libpgsd.pgsd_open(&self._handle, c_name, c_flags)
+                err = errno
+        _raise_on_error(retval, name, err)
         self._is_open = True
 
         if schema is not None:
@@ -138,11 +194,14 @@ class PGSDFile:
     # ------------------------------------------------------------------ life cycle
     def close(self, write_all=True):
         """Close the file; further operations raise ValueError (ref: fl.pyx:382-458)."""
+        cdef int retval, err
         if self._is_open:
             logger.info('closing file: ' + self._name)
-            retval = self._lib.pgsd_close(C.byref(self._handle))
+            with nogil:
+                retval = libpgsd.pgsd_close(&self._handle)
+                err = errno
             self._is_open = False
-            _raise_on_error(retval, self._name)
+            _raise_on_error(retval, self._name, err)
 
     def end_frame(self, write_all=True):
         """Complete the current frame (ref: fl.pyx:460-505).
@@ -150,27 +209,44 @@ class PGSDFile:
         With several ranks this is where the frame's chunks get their file offsets: one
         all-gather of the chunk sizes + exclusive scan (K2) instead of per-chunk collectives.
         """
+        cdef int retval, err
         self._check_open()
-        logger.debug('end frame: ' + self._name)
-        _raise_on_error(self._lib.pgsd_end_frame(C.byref(self._handle)), self._name)
+        with nogil:
+            retval = libpgsd.pgsd_end_frame(&self._handle)
+            err = errno
+        _raise_on_error(retval, self._name, err)
 
     def flush(self, write_all=True):
         """Flush all buffered frames to the file and wait for queued device writes (ref: fl.pyx:507-524)."""
+        cdef int retval, err
         self._check_open()
-        logger.debug('flush: ' + self._name)
-        _raise_on_error(self._lib.pgsd_flush(C.byref(self._handle)), self._name)
+        with nogil:
+            retval = libpgsd.pgsd_flush(&self._handle)
+            err = errno
+        _raise_on_error(retval, self._name, err)
 
     # ------------------------------------------------------------------ write
-    def _offset_args(self, N, M, offset, rank):
+    cdef _offset_args(self, N, M, offset, rank):
         # ref: fl.pyx:594-598 -- `offset` holds the row counts of all ranks
         if offset is None:
             return N, 0
         if isinstance(offset, str):
             if offset != 'auto':
                 raise ValueError("offset must be None, 'auto' or an array of per-rank row counts")
-            return _lib.N_GLOBAL_AUTO, _lib.OFFSET_AUTO
+            return _AUTO, _AUTO
         offset = numpy.asarray(offset)
         return int(offset.sum()), int(M) * int(offset[0:rank].sum())
+
+    cdef int _c_write(self, bytes bname, int pgsd_type, uint64_t N, uint32_t M, uint64_t N_global, uint64_t stride,
+                      bint write_all, uintptr_t ptr, int* err) noexcept:
+        cdef const char* c_name = bname
+        cdef uint64_t gsize = 0 if N_global == _AUTO else N_global * M
+        cdef int retval
+        with nogil:
+            retval = libpgsd.pgsd_write_chunk(&self._handle, c_name, <libpgsd.pgsd_type>pgsd_type, N, M, N_global, M,
+                                              stride, gsize, write_all, 0, <const void*>ptr)
+            err[0] = errno
+        return retval
 
     def write_chunk(self, name, data, offset=None, rank=0, write_all=True):
         """Write a data chunk to the current frame (ref: fl.pyx:526-654).
@@ -185,6 +261,9 @@ class PGSDFile:
             write_all (bool): every rank writes its rows (True, the reference default) or the
                 chunk is replicated/small and goes through the write buffer (False).
         """
+        cdef Py_buffer buf
+        cdef int retval, err = 0
+        cdef uintptr_t ptr = 0
         self._check_open()
         if is_device_array(data):
             return self._write_chunk_device(name, data, offset, rank, write_all)
@@ -202,14 +281,25 @@ class PGSDFile:
         pgsd_type = _NP_TO_PGSD.get(data_array.dtype)
         if pgsd_type is None:
             raise ValueError("invalid type for chunk: " + name)
-        data_ptr = data_array.ctypes.data if data_array.size else None
-        logger.debug('write chunk: ' + self._name + ' - ' + name)
-        gsize = 0 if N_global == _lib.N_GLOBAL_AUTO else N_global * M
-        retval = self._lib.pgsd_write_chunk(C.byref(self._handle), name.encode('utf-8'), pgsd_type, N, M,
-                                            N_global, M, stride, gsize, bool(write_all), 0, data_ptr)
-        _raise_on_error(retval, self._name)
+        if data_array.size:
+            PyObject_GetBuffer(data_array, &buf, PyBUF_SIMPLE)
+            ptr = <uintptr_t>buf.buf
+            try:
+                retval = self._c_write(name.encode('utf-8'), pgsd_type, N, M, N_global, stride, bool(write_all), ptr, &err)
+            finally:
+                PyBuffer_Release(&buf)
+        else:
+            retval = self._c_write(name.encode('utf-8'), pgsd_type, N, M, N_global, stride, bool(write_all), 0, &err)
+        _raise_on_error(retval, self._name, err)
 
     def _write_chunk_device(self, name, data, offset, rank, write_all):
+        cdef libpgsd.pgsd_b200_column cols[8]
+        cdef int retval, err = 0, j
+        cdef const char* c_name
+        cdef uint64_t cN, cNg, cstride
+        cdef uint32_t cM
+        cdef int ctype
+        cdef bint call
         ptr, shape, dtype, strides, keep = as_device_view(data)
         if len(shape) > 2:
             raise ValueError("PGSD can only write 1 or 2 dimensional arrays: " + name)
@@ -221,70 +311,30 @@ class PGSDFile:
         N_global, stride = self._offset_args(N, M, offset, rank)
         item = dtype.itemsize
         contiguous = strides is None or tuple(strides) == ((M * item, item) if len(shape) == 2 else (item,))
-        logger.debug('write chunk (device): ' + self._name + ' - ' + name)
+        bname = name.encode('utf-8')
         if contiguous or N == 0:
-            gsize = 0 if N_global == _lib.N_GLOBAL_AUTO else N_global * M
-            retval = self._lib.pgsd_write_chunk(C.byref(self._handle), name.encode('utf-8'), pgsd_type, N, M,
-                                                N_global, M, stride, gsize, bool(write_all), 0,
-                                                ptr if N else None)
+            retval = self._c_write(bname, pgsd_type, N, M, N_global, stride, bool(write_all), <uintptr_t>(ptr if N else 0),
+                                   &err)
         else:
             # strided device array: K1 makes it contiguous (device-side ascontiguousarray)
             if M > 8 or any(s % item for s in strides):
                 raise ValueError("strided device arrays need M <= 8 and element-aligned strides: " + name)
             logger.warning('implicit device pack when writing chunk: ' + name)
             col_stride = strides[1] if len(shape) == 2 else item
-            cols = (_lib.Column * M)(*[_lib.Column(ptr + j * col_stride, strides[0] // item) for j in range(M)])
-            retval = self._lib.pgsd_b200_write_chunk_soa(C.byref(self._handle), name.encode('utf-8'), pgsd_type,
-                                                         N, M, N_global, M, stride, bool(write_all), pgsd_type, cols)
+            for j in range(M):
+                cols[j].base = <const void*><uintptr_t>(ptr + j * col_stride)
+                cols[j].stride = strides[0] // item
+            c_name = bname
+            cN, cM, cNg, cstride, ctype, call = N, M, N_global, stride, pgsd_type, bool(write_all)
+            with nogil:
+                retval = libpgsd.pgsd_b200_write_chunk_soa(&self._handle, c_name, <libpgsd.pgsd_type>ctype, cN, cM, cNg, cM,
+                                                           cstride, call, <libpgsd.pgsd_type>ctype, cols)
+                err = errno
         del keep
-        _raise_on_error(retval, self._name)
-
-    def write_chunk_soa(self, name, columns, dtype=None, offset=None, rank=0, write_all=True):
-        """Pack M component arrays into one (N, M) chunk on the device and write it (K1).
-
-        ``columns`` is a sequence of M equally long 1-D arrays of one dtype -- CUDA arrays (hot
-        path) or numpy arrays (uploaded first).  ``dtype`` is the chunk's dtype (default: the
-        columns' dtype); the cast follows ``numpy.astype``.  This is the device form of
-        ``numpy.ascontiguousarray(numpy.stack(columns, 1), dtype)`` -- what the reference's
-        callers do on the host before ``write_chunk`` (fl.pyx:571, hoomd.py:206-270).
-        """
-        self._check_open()
-        M = len(columns)
-        if M < 1 or M > 8:
-            raise ValueError("write_chunk_soa takes 1..8 columns: " + name)
-        views, keep = [], []
-        for c in columns:
-            if is_device_array(c):
-                ptr, shape, cdt, strides, k = as_device_view(c)
-                keep.append(k)
-                on_device = True
-            else:
-                a = numpy.asarray(c)
-                ptr, shape, cdt, strides = a.ctypes.data, a.shape, a.dtype, a.strides
-                keep.append(a)
-                on_device = False
-            if len(shape) != 1:
-                raise ValueError("write_chunk_soa columns must be 1-dimensional: " + name)
-            st = cdt.itemsize if strides is None else strides[0]
-            if st % cdt.itemsize:
-                raise ValueError("column stride is not a multiple of the item size: " + name)
-            views.append((ptr, int(shape[0]), cdt, st // cdt.itemsize, on_device))
-        N, src_dt = views[0][1], views[0][2]
-        if any(v[1] != N or v[2] != src_dt or v[4] != views[0][4] for v in views):
-            raise ValueError("write_chunk_soa columns must share length, dtype and memory space: " + name)
-        src_type = _NP_TO_PGSD.get(src_dt)
-        dst_type = _NP_TO_PGSD.get(numpy.dtype(dtype) if dtype is not None else src_dt)
-        if src_type is None or dst_type is None:
-            raise ValueError("invalid type for chunk: " + name)
-        N_global, stride = self._offset_args(N, M, offset, rank)
-        cols = (_lib.Column * M)(*[_lib.Column(v[0] if N else None, v[3]) for v in views])
-        retval = self._lib.pgsd_b200_write_chunk_soa(C.byref(self._handle), name.encode('utf-8'), dst_type, N, M,
-                                                     N_global, M, stride, bool(write_all), src_type, cols)
-        del keep
-        _raise_on_error(retval, self._name)
+        _raise_on_error(retval, self._name, err)
 
     def _soa_views(self, name, columns):
-        """-> (M x (ptr, stride), N, src dtype, keep-alive list) for 1..8 equally long 1-D columns."""
+        """-> (M x (ptr, N, dtype, stride, on_device), N, src dtype, keep-alive list)."""
         M = len(columns)
         if M < 1 or M > 8:
             raise ValueError("write_chunk_soa takes 1..8 columns: " + name)
@@ -310,6 +360,19 @@ class PGSDFile:
             raise ValueError("write_chunk_soa columns must share length, dtype and memory space: " + name)
         return views, N, src_dt, keep
 
+    def write_chunk_soa(self, name, columns, dtype=None, offset=None, rank=0, write_all=True):
+        """Pack M component arrays into one (N, M) chunk on the device and write it (K1).
+
+        ``columns`` is a sequence of M equally long 1-D arrays of one dtype -- CUDA arrays (hot
+        path) or numpy arrays (uploaded first).  ``dtype`` is the chunk's dtype (default: the
+        columns' dtype); the cast follows ``numpy.astype``.  This is the device form of
+        ``numpy.ascontiguousarray(numpy.stack(columns, 1), dtype)`` -- what the reference's
+        callers do on the host before ``write_chunk`` (fl.pyx:571, hoomd.py:206-270).
+        """
+        self._check_open()
+        prepared = self.prepare_frame_soa([(name, columns, dtype, offset, write_all)], rank=rank)
+        self.write_frame_soa(prepared)
+
     def prepare_frame_soa(self, chunks, rank=0):
         """Build the reusable C descriptor table for :py:meth:`write_frame_soa`.
 
@@ -317,39 +380,68 @@ class PGSDFile:
         :py:meth:`write_chunk_soa`'s arguments.  The returned object keeps the arrays alive and can
         be written any number of times (one simulation's buffers, one frame per time step).
         """
-        n = len(chunks)
-        descs = (_lib.ChunkDesc * max(n, 1))()
+        cdef _PreparedFrame pf = _PreparedFrame()
+        cdef int n = len(chunks), i, j, ncols = 0, c0 = 0
         keep = []
-        for i, (name, columns, dtype, offset, write_all) in enumerate(chunks):
+        parsed = []
+        for (name, columns, dtype, offset, write_all) in chunks:
             views, N, src_dt, k = self._soa_views(name, columns)
-            M = len(views)
             src_type = _NP_TO_PGSD.get(src_dt)
             dst_type = _NP_TO_PGSD.get(numpy.dtype(dtype) if dtype is not None else src_dt)
             if src_type is None or dst_type is None:
                 raise ValueError("invalid type for chunk: " + name)
-            N_global, stride = self._offset_args(N, M, offset, rank)
-            cols = (_lib.Column * M)(*[_lib.Column(v[0] if N else None, v[3]) for v in views])
+            N_global, stride = self._offset_args(N, len(views), offset, rank)
             bname = name.encode('utf-8')
-            keep.extend([k, cols, bname])
-            descs[i] = _lib.ChunkDesc(bname, dst_type, src_type, N, M, N_global, M, stride, bool(write_all),
-                                      cols)
-        return (descs, n, keep)
+            keep.extend([k, bname])
+            parsed.append((bname, views, N, src_type, dst_type, N_global, stride, bool(write_all)))
+            ncols += len(views)
+        pf.descs = <libpgsd.pgsd_b200_chunk_desc*>malloc(max(n, 1) * sizeof(libpgsd.pgsd_b200_chunk_desc))
+        pf.cols = <libpgsd.pgsd_b200_column*>malloc(max(ncols, 1) * sizeof(libpgsd.pgsd_b200_column))
+        if pf.descs == NULL or pf.cols == NULL:
+            raise MemoryError()
+        memset(pf.descs, 0, max(n, 1) * sizeof(libpgsd.pgsd_b200_chunk_desc))
+        for i in range(n):
+            bname, views, N, src_type, dst_type, N_global, stride, wa = parsed[i]
+            for j in range(len(views)):
+                pf.cols[c0 + j].base = <const void*><uintptr_t>(views[j][0] if N else 0)
+                pf.cols[c0 + j].stride = views[j][3]
+            pf.descs[i].name = <const char*>bname
+            pf.descs[i].dst_type = <libpgsd.pgsd_type><int>dst_type
+            pf.descs[i].src_type = <libpgsd.pgsd_type><int>src_type
+            pf.descs[i].N = N
+            pf.descs[i].M = len(views)
+            pf.descs[i].N_global = N_global
+            pf.descs[i].M_global = len(views)
+            pf.descs[i].offset = stride
+            pf.descs[i].all = wa
+            pf.descs[i].cols = pf.cols + c0
+            c0 += len(views)
+        pf.n = n
+        pf.keep = keep
+        return pf
 
-    def write_frame_soa(self, prepared):
+    def write_frame_soa(self, _PreparedFrame prepared):
         """Write all SoA chunks of a frame with ONE K1 launch (``pgsd_b200_write_chunks_soa``);
         ``prepared`` comes from :py:meth:`prepare_frame_soa`.  Equivalent to calling
         :py:meth:`write_chunk_soa` for each chunk in order."""
+        cdef int retval, err
         self._check_open()
-        descs, n, _ = prepared
-        _raise_on_error(self._lib.pgsd_b200_write_chunks_soa(C.byref(self._handle), n, descs), self._name)
+        with nogil:
+            retval = libpgsd.pgsd_b200_write_chunks_soa(&self._handle, prepared.n, prepared.descs)
+            err = errno
+        _raise_on_error(retval, self._name, err)
 
     # ------------------------------------------------------------------ read
     def chunk_exists(self, frame, name, write_all=True):
         """Test if a chunk exists (ref: fl.pyx:656-715)."""
+        cdef const libpgsd.pgsd_index_entry* entry
+        cdef bytes bname = name.encode('utf-8')
+        cdef const char* c_name = bname
+        cdef uint64_t c_frame = frame
         self._check_open()
-        logger.debug('chunk exists: ' + self._name + ' - ' + name)
-        entry = self._lib.pgsd_find_chunk(C.byref(self._handle), int(frame), name.encode('utf-8'))
-        return bool(entry)
+        with nogil:
+            entry = libpgsd.pgsd_find_chunk(&self._handle, c_frame, c_name)
+        return entry != NULL
 
     def read_chunk(self, frame, name, N=0, M=0, offset=0, r_all=False, device=False):
         """Read a data chunk (ref: fl.pyx:717-874).
@@ -360,11 +452,23 @@ class PGSDFile:
         ``device=True`` returns a :py:class:`~pgsd_sph_b200.devmem.DeviceArray`.
         Raises KeyError if the chunk does not exist.
         """
+        cdef const libpgsd.pgsd_index_entry* entry_p
+        cdef libpgsd.pgsd_index_entry entry
+        cdef bytes bname = name.encode('utf-8')
+        cdef const char* c_name = bname
+        cdef uint64_t c_frame = frame
+        cdef Py_buffer buf
+        cdef uintptr_t ptr
+        cdef uint64_t c_rows
+        cdef uint32_t c_cols, c_off
+        cdef bint c_all = bool(r_all)
+        cdef int retval = 0, err = 0
         self._check_open()
-        entry_p = self._lib.pgsd_find_chunk(C.byref(self._handle), int(frame), name.encode('utf-8'))
-        if not entry_p:
+        with nogil:
+            entry_p = libpgsd.pgsd_find_chunk(&self._handle, c_frame, c_name)
+        if entry_p == NULL:
             raise KeyError("frame " + str(frame) + " / chunk " + name + " not found in: " + self._name)
-        entry = _lib.IndexEntry.from_buffer_copy(entry_p.contents)
+        entry = entry_p[0]
         dtype = _PGSD_TO_NP.get(entry.type)
         if dtype is None:
             raise ValueError("invalid type for chunk: " + name)
@@ -372,31 +476,44 @@ class PGSDFile:
         cols = int(M) if r_all else int(entry.M)
         if r_all and cols != entry.M:
             raise ValueError("M must equal the chunk's M for a partial read: " + name)
-        logger.debug('read chunk: ' + self._name + ' - ' + str(frame) + ' - ' + name)
+        c_rows, c_cols, c_off = rows, cols, int(offset)
         if device:
             out = DeviceArray((rows, cols), dtype)
-            ptr = out.ptr
+            ptr = <uintptr_t>out.ptr
+            if rows != 0 and cols != 0:
+                with nogil:
+                    retval = libpgsd.pgsd_read_chunk(&self._handle, <void*>ptr, &entry, c_rows, c_cols, c_off, c_all)
+                    err = errno
         else:
             out = numpy.empty(dtype=dtype, shape=[rows, cols])
-            ptr = out.ctypes.data
-        # only read chunk if we have data
-        if rows != 0 and cols != 0:
-            retval = self._lib.pgsd_read_chunk(C.byref(self._handle), ptr, C.byref(entry), rows, cols,
-                                               int(offset), bool(r_all))
-            _raise_on_error(retval, self._name)
+            # only read chunk if we have data
+            if rows != 0 and cols != 0:
+                PyObject_GetBuffer(out, &buf, PyBUF_WRITABLE)
+                ptr = <uintptr_t>buf.buf
+                try:
+                    with nogil:
+                        retval = libpgsd.pgsd_read_chunk(&self._handle, <void*>ptr, &entry, c_rows, c_cols, c_off, c_all)
+                        err = errno
+                finally:
+                    PyBuffer_Release(&buf)
+        _raise_on_error(retval, self._name, err)
         if entry.M == 1:
             return out.reshape([rows])
         return out
 
     def find_matching_chunk_names(self, match, write_all=True):
         """All chunk names in the file that start with ``match`` (ref: fl.pyx:876-945)."""
+        cdef bytes bmatch = match.encode('utf-8')
+        cdef const char* c_match = bmatch
+        cdef const char* found
         self._check_open()
-        c_match = match.encode('utf-8')
         retval = []
-        found = self._lib.pgsd_find_matching_chunk_name(C.byref(self._handle), c_match, None)
-        while found:
-            retval.append(C.string_at(found).decode('utf-8'))
-            found = self._lib.pgsd_find_matching_chunk_name(C.byref(self._handle), c_match, found)
+        with nogil:
+            found = libpgsd.pgsd_find_matching_chunk_name(&self._handle, c_match, NULL)
+        while found != NULL:
+            retval.append(found.decode('utf-8'))
+            with nogil:
+                found = libpgsd.pgsd_find_matching_chunk_name(&self._handle, c_match, found)
         return retval
 
     # ------------------------------------------------------------------ protocol / properties
@@ -426,12 +543,12 @@ class PGSDFile:
 
     @property
     def pgsd_version(self):
-        v = self._handle.header.pgsd_version
+        cdef uint32_t v = self._handle.header.pgsd_version
         return (v >> 16, v & 0xffff)
 
     @property
     def schema_version(self):
-        v = self._handle.header.schema_version
+        cdef uint32_t v = self._handle.header.schema_version
         return (v >> 16, v & 0xffff)
 
     @property
@@ -445,38 +562,34 @@ class PGSDFile:
     @property
     def nframes(self):
         self._check_open()
-        return self._lib.pgsd_get_nframes(C.byref(self._handle))
+        return libpgsd.pgsd_get_nframes(&self._handle)
 
     @property
     def nnames(self):
         self._check_open()
-        return self._lib.pgsd_get_nnames(C.byref(self._handle))
+        return libpgsd.pgsd_get_nnames(&self._handle)
 
     @property
     def maximum_write_buffer_size(self):
         self._check_open()
-        return self._lib.pgsd_get_maximum_write_buffer_size(C.byref(self._handle))
+        return libpgsd.pgsd_get_maximum_write_buffer_size(&self._handle)
 
     @maximum_write_buffer_size.setter
     def maximum_write_buffer_size(self, size):
         self._check_open()
-        _raise_on_error(self._lib.pgsd_set_maximum_write_buffer_size(C.byref(self._handle), int(size)), self._name)
+        _raise_on_error(libpgsd.pgsd_set_maximum_write_buffer_size(&self._handle, int(size)), self._name)
 
     @property
     def index_entries_to_buffer(self):
         self._check_open()
-        return self._lib.pgsd_get_index_entries_to_buffer(C.byref(self._handle))
+        return libpgsd.pgsd_get_index_entries_to_buffer(&self._handle)
 
     @index_entries_to_buffer.setter
     def index_entries_to_buffer(self, number):
         self._check_open()
-        _raise_on_error(self._lib.pgsd_set_index_entries_to_buffer(C.byref(self._handle), int(number)), self._name)
+        _raise_on_error(libpgsd.pgsd_set_index_entries_to_buffer(&self._handle, int(number)), self._name)
 
-    def __del__(self):
-        try:
-            if self._is_open:
-                logger.info('closing file: ' + self._name)
-                self._lib.pgsd_close(C.byref(self._handle))
-                self._is_open = False
-        except Exception:
-            pass
+    def __dealloc__(self):
+        if self._is_open:
+            libpgsd.pgsd_close(&self._handle)
+            self._is_open = False

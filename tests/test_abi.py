@@ -59,7 +59,7 @@ def test_no_oracle_import_in_product():
     pkg = os.path.join(REPO, "pgsd_sph_b200")
     for root, _, files in os.walk(pkg):
         for f in files:
-            if f.endswith((".py", ".cpp", ".cu", ".h")):
+            if f.endswith((".py", ".pyx", ".pxd", ".cpp", ".cu", ".h")):
                 text = open(os.path.join(root, f), errors="replace").read()
                 assert "import oracle" not in text and "from oracle" not in text, f
                 assert "oracle/" not in text.replace("oracle/ref_driver.c's", "") or f in ("synth.py",), f
