@@ -245,10 +245,9 @@ struct TileRankSmem
 
 template <int ITEMS, int RM>
 __device__ __forceinline__ void tile_rank(const uint32_t (&key)[ITEMS], uint32_t (&pos)[ITEMS], uint32_t tile_n,
-                                          int shift, const TileRankSmem& sm, uint32_t ntiles,
-                                          const uint32_t* __restrict__ tile_offset,
-                                          const unsigned long long* __restrict__ digit_base)
+                                          int shift, const TileRankSmem& sm, unsigned long long my_gbase)
     {
+    // my_gbase (threads < RADIX): global output position of this tile's first key with digit `tid`
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const uint32_t wbase = (uint32_t)w * (32 * ITEMS);
     for (int i = tid; i < SORT_WARPS * RADIX; i += SORT_THREADS)
@@ -331,8 +330,7 @@ __device__ __forceinline__ void tile_rank(const uint32_t (&key)[ITEMS], uint32_t
             b += sm.wtot[j];
         const uint32_t start = total + b;
         sm.dstart[tid] = start;
-        sm.gdelta[tid] = digit_base[tid] + (unsigned long long)tile_offset[(size_t)tid * ntiles + blockIdx.x]
-                         - (unsigned long long)start;
+        sm.gdelta[tid] = my_gbase - (unsigned long long)start;
         }
     __syncthreads();
 #pragma unroll
@@ -343,13 +341,27 @@ __device__ __forceinline__ void tile_rank(const uint32_t (&key)[ITEMS], uint32_t
         }
     }
 
+// Tile table of the segmented pair passes: after the bucket pass every bucket is sorted on its own
+// (low key bits only), so tiles never straddle buckets and no final pass over the bucket digit is needed.
+struct SegTables
+    {
+    const uint32_t* tile_begin; // first key of tile t
+    const uint32_t* tile_cnt;   // keys in tile t (<= SORT_TILE)
+    const uint32_t* tile_bkt;   // bucket of tile t
+    const uint32_t* ntiles;     // [0] = number of tiles actually used
+    const uint32_t* bstart;     // bucket start (257 entries)
+    const uint32_t* bbase;      // [bucket * 256 + digit]: keys of the bucket with a smaller digit
+    uint32_t stride;            // row stride of counts[] (upper bound of the tile count)
+    };
+
 // pair pass.  FIRST: the index payload is implicit (idx = global position), saving its read.
-template <bool FIRST, int RM>
+// SEG: tiles and output positions come from the per-bucket tables above.
+template <bool FIRST, int RM, bool SEG>
 __global__ void __launch_bounds__(SORT_THREADS, 2)
     k4_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ idx_in,
                uint32_t* __restrict__ keys_out, uint32_t* __restrict__ idx_out, uint64_t n, int shift,
                uint32_t ntiles, const uint32_t* __restrict__ tile_offset,
-               const unsigned long long* __restrict__ digit_base)
+               const unsigned long long* __restrict__ digit_base, const SegTables seg)
     {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // one pad word per 32: with exactly 32 keys per digit in a tile (dense ids in the later passes)
@@ -364,8 +376,29 @@ __global__ void __launch_bounds__(SORT_THREADS, 2)
     sm.wtot = wtot;
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const uint64_t tile_base = (uint64_t)blockIdx.x * SORT_TILE;
-    const uint32_t tile_n = (uint32_t)((n - tile_base) < (uint64_t)SORT_TILE ? (n - tile_base) : SORT_TILE);
+    uint64_t tile_base;
+    uint32_t tile_n;
+    unsigned long long my_gbase = 0;
+    if (SEG)
+        {
+        if (blockIdx.x >= seg.ntiles[0])
+            return;
+        tile_base = seg.tile_begin[blockIdx.x];
+        tile_n = seg.tile_cnt[blockIdx.x];
+        if (tid < RADIX)
+            {
+            const uint32_t b = seg.tile_bkt[blockIdx.x];
+            my_gbase = (unsigned long long)seg.bstart[b] + seg.bbase[b * RADIX + tid]
+                       + tile_offset[(size_t)tid * seg.stride + blockIdx.x];
+            }
+        }
+    else
+        {
+        tile_base = (uint64_t)blockIdx.x * SORT_TILE;
+        tile_n = (uint32_t)((n - tile_base) < (uint64_t)SORT_TILE ? (n - tile_base) : SORT_TILE);
+        if (tid < RADIX)
+            my_gbase = digit_base[tid] + (unsigned long long)tile_offset[(size_t)tid * ntiles + blockIdx.x];
+        }
     const uint32_t wbase = (uint32_t)w * (32 * SORT_ITEMS);
 
     uint32_t key[SORT_ITEMS], pos[SORT_ITEMS];
@@ -375,7 +408,7 @@ __global__ void __launch_bounds__(SORT_THREADS, 2)
         const uint32_t e = wbase + k * 32 + lane;
         key[k] = e < tile_n ? ld_stream_u32(keys_in + tile_base + e) : 0xffffffffu;
         }
-    tile_rank<SORT_ITEMS, RM>(key, pos, tile_n, shift, sm, ntiles, tile_offset, digit_base);
+    tile_rank<SORT_ITEMS, RM>(key, pos, tile_n, shift, sm, my_gbase);
     // the index payload is fetched only now (keeps the ranking loop's register footprint small);
     // all loads of the batch are issued before the first shared-memory store consumes one
     uint32_t src[SORT_ITEMS];
@@ -414,6 +447,135 @@ __global__ void __launch_bounds__(SORT_THREADS, 2)
             idx_out[g] = sidx[jp];
             }
         }
+    }
+
+// ---- tables of the segmented passes --------------------------------------------------------------
+// one CTA of 256 threads, thread b = bucket b: tile counts, their exclusive scan, tile descriptors
+__global__ void __launch_bounds__(RADIX)
+    k4s_setup(const unsigned long long* __restrict__ bucket_base, uint64_t n, uint32_t* __restrict__ bstart,
+              uint32_t* __restrict__ tile_first, uint32_t* __restrict__ tile_begin, uint32_t* __restrict__ tile_cnt,
+              uint32_t* __restrict__ tile_bkt, uint32_t* __restrict__ ntiles_out)
+    {
+    __shared__ uint32_t s[RADIX];
+    const int b = threadIdx.x;
+    const uint32_t begin = (uint32_t)bucket_base[b];
+    const uint32_t end = b + 1 < RADIX ? (uint32_t)bucket_base[b + 1] : (uint32_t)n;
+    const uint32_t size = end - begin;
+    const uint32_t nt = (size + SORT_TILE - 1) / SORT_TILE;
+    s[b] = nt;
+    __syncthreads();
+    if (b == 0)
+        {
+        uint32_t acc = 0;
+        for (int i = 0; i < RADIX; i++)
+            {
+            const uint32_t c = s[i];
+            s[i] = acc;
+            acc += c;
+            }
+        ntiles_out[0] = acc;
+        tile_first[RADIX] = acc;
+        bstart[RADIX] = (uint32_t)n;
+        }
+    __syncthreads();
+    const uint32_t first = s[b];
+    bstart[b] = begin;
+    tile_first[b] = first;
+    for (uint32_t i = 0; i < nt; i++)
+        {
+        tile_begin[first + i] = begin + i * SORT_TILE;
+        tile_cnt[first + i] = size - i * SORT_TILE < (uint32_t)SORT_TILE ? size - i * SORT_TILE : SORT_TILE;
+        tile_bkt[first + i] = (uint32_t)b;
+        }
+    }
+
+__global__ void __launch_bounds__(SORT_THREADS)
+    k4s_histogram(const uint32_t* __restrict__ keys, int shift, const SegTables seg, uint32_t* __restrict__ counts)
+    {
+    if (blockIdx.x >= seg.ntiles[0])
+        return;
+    __shared__ unsigned int h[SORT_WARPS / 4][RADIX];
+    for (int i = threadIdx.x; i < (SORT_WARPS / 4) * RADIX; i += SORT_THREADS)
+        (&h[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t base = seg.tile_begin[blockIdx.x], cnt = seg.tile_cnt[blockIdx.x];
+    unsigned int* mine = h[(threadIdx.x >> 5) & (SORT_WARPS / 4 - 1)];
+    uint32_t v[SORT_ITEMS];
+#pragma unroll
+    for (int k = 0; k < SORT_ITEMS; k++)
+        {
+        const uint32_t e = threadIdx.x + k * SORT_THREADS;
+        v[k] = e < cnt ? ld_stream_u32(keys + base + e) : 0u;
+        }
+#pragma unroll
+    for (int k = 0; k < SORT_ITEMS; k++)
+        if (threadIdx.x + k * SORT_THREADS < cnt)
+            atomicAdd(&mine[(v[k] >> shift) & 255u], 1u);
+    __syncthreads();
+    for (int d = threadIdx.x; d < RADIX; d += SORT_THREADS)
+        {
+        unsigned int c = 0;
+#pragma unroll
+        for (int q = 0; q < SORT_WARPS / 4; q++)
+            c += h[q][d];
+        counts[(size_t)d * seg.stride + blockIdx.x] = c;
+        }
+    }
+
+// CTA d = digit d; warp w scans the tiles of buckets w, w+8, ... (exclusive, in place) and records
+// the bucket's total for the digit
+__global__ void __launch_bounds__(256)
+    k4s_scan(uint32_t* __restrict__ counts, const uint32_t* __restrict__ tile_first, uint32_t stride,
+             uint32_t* __restrict__ btot)
+    {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t* row = counts + (size_t)blockIdx.x * stride;
+    for (int b = w; b < RADIX; b += 8)
+        {
+        const uint32_t t0 = tile_first[b], t1 = tile_first[b + 1];
+        uint32_t carry = 0;
+        for (uint32_t s = t0; s < t1; s += 32)
+            {
+            const uint32_t i = s + lane;
+            const uint32_t v = i < t1 ? row[i] : 0u;
+            uint32_t x = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+                {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= o)
+                    x += y;
+                }
+            if (i < t1)
+                row[i] = carry + x - v;
+            carry += __shfl_sync(0xffffffffu, x, 31);
+            }
+        if (lane == 0)
+            btot[b * RADIX + blockIdx.x] = carry;
+        }
+    }
+
+// CTA b = bucket b: exclusive scan over the digits of the bucket's totals
+__global__ void __launch_bounds__(RADIX) k4s_base(const uint32_t* __restrict__ btot, uint32_t* __restrict__ bbase)
+    {
+    __shared__ uint32_t ws[8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t v = btot[blockIdx.x * RADIX + threadIdx.x];
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+        {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o)
+            x += y;
+        }
+    if (lane == 31)
+        ws[w] = x;
+    __syncthreads();
+    uint32_t add = 0;
+    for (int j = 0; j < w; j++)
+        add += ws[j];
+    bbase[blockIdx.x * RADIX + threadIdx.x] = add + x - v;
     }
 
 constexpr size_t SCATTER_SMEM
@@ -467,7 +629,9 @@ __global__ void __launch_bounds__(SORT_THREADS)
         const uint32_t e = wbase + k * 32 + lane;
         key[k] = e < tile_n ? ld_stream_u32(keys_in + tile_base + e) : 0xffffffffu;
         }
-    tile_rank<ROWS_ITEMS, RM>(key, pos, tile_n, shift, sm, ntiles, tile_offset, digit_base);
+    const unsigned long long my_gbase
+        = tid < RADIX ? digit_base[tid] + (unsigned long long)tile_offset[(size_t)tid * ntiles + blockIdx.x] : 0ull;
+    tile_rank<ROWS_ITEMS, RM>(key, pos, tile_n, shift, sm, my_gbase);
 #pragma unroll
     for (int k = 0; k < ROWS_ITEMS; k++)
         {
@@ -707,7 +871,9 @@ __global__ void __launch_bounds__(SORT_THREADS, 2)
         const uint32_t e = wbase + k * 32 + lane;
         key[k] = e < tile_n ? ld_stream_u32(keys_in + tile_base + e) : 0xffffffffu;
         }
-    tile_rank<ITEMS, RM>(key, pos, tile_n, shift, sm, ntiles, tile_offset, digit_base);
+    const unsigned long long my_gbase
+        = tid < RADIX ? digit_base[tid] + (unsigned long long)tile_offset[(size_t)tid * ntiles + blockIdx.x] : 0ull;
+    tile_rank<ITEMS, RM>(key, pos, tile_n, shift, sm, my_gbase);
 #pragma unroll
     for (int k = 0; k < ITEMS; k++)
         {
@@ -1120,10 +1286,14 @@ static int sort_setup()
     static bool attr_done = false;
     if (!attr_done)
         {
-        cudaFuncSetAttribute(k4_scatter<true, RANK_BALLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCATTER_SMEM);
-        cudaFuncSetAttribute(k4_scatter<false, RANK_BALLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCATTER_SMEM);
-        cudaFuncSetAttribute(k4_scatter<true, RANK_MATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCATTER_SMEM);
-        cudaFuncSetAttribute(k4_scatter<false, RANK_MATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCATTER_SMEM);
+        cudaFuncSetAttribute(k4_scatter<true, RANK_BALLOT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCATTER_SMEM);
+        cudaFuncSetAttribute(k4_scatter<false, RANK_BALLOT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCATTER_SMEM);
+        cudaFuncSetAttribute(k4_scatter<true, RANK_MATCH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCATTER_SMEM);
+        cudaFuncSetAttribute(k4_scatter<false, RANK_MATCH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCATTER_SMEM);
+        cudaFuncSetAttribute(k4_scatter<true, RANK_BALLOT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCATTER_SMEM);
+        cudaFuncSetAttribute(k4_scatter<false, RANK_BALLOT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCATTER_SMEM);
+        cudaFuncSetAttribute(k4_scatter<true, RANK_MATCH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCATTER_SMEM);
+        cudaFuncSetAttribute(k4_scatter<false, RANK_MATCH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCATTER_SMEM);
         cudaFuncSetAttribute(k4_bucket_rows<RANK_BALLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ROWS_SMEM);
         cudaFuncSetAttribute(k4_bucket_rows<RANK_MATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ROWS_SMEM);
         const int big = 200 * 1024;
@@ -1223,23 +1393,25 @@ static int key_census(uint64_t n, const uint32_t* keys, const PassTables& t, cud
     return 0;
     }
 
+template <bool SEG>
 static void launch_scatter(bool first, const uint32_t* kin, const uint32_t* iin, uint32_t* kout, uint32_t* iout,
-                           uint64_t n, int shift, uint32_t ntiles, const PassTables& t, cudaStream_t st)
+                           uint64_t n, int shift, uint32_t ntiles, const uint32_t* counts,
+                           const unsigned long long* digit_base, const SegTables& seg, cudaStream_t st)
     {
     const bool m = rank_mode() == RANK_MATCH;
     if (first)
         {
         if (m)
-            k4_scatter<true, RANK_MATCH><<<ntiles, SORT_THREADS, SCATTER_SMEM, st>>>(kin, iin, kout, iout, n, shift, ntiles, t.counts, t.digit_base);
+            k4_scatter<true, RANK_MATCH, SEG><<<ntiles, SORT_THREADS, SCATTER_SMEM, st>>>(kin, iin, kout, iout, n, shift, ntiles, counts, digit_base, seg);
         else
-            k4_scatter<true, RANK_BALLOT><<<ntiles, SORT_THREADS, SCATTER_SMEM, st>>>(kin, iin, kout, iout, n, shift, ntiles, t.counts, t.digit_base);
+            k4_scatter<true, RANK_BALLOT, SEG><<<ntiles, SORT_THREADS, SCATTER_SMEM, st>>>(kin, iin, kout, iout, n, shift, ntiles, counts, digit_base, seg);
         }
     else
         {
         if (m)
-            k4_scatter<false, RANK_MATCH><<<ntiles, SORT_THREADS, SCATTER_SMEM, st>>>(kin, iin, kout, iout, n, shift, ntiles, t.counts, t.digit_base);
+            k4_scatter<false, RANK_MATCH, SEG><<<ntiles, SORT_THREADS, SCATTER_SMEM, st>>>(kin, iin, kout, iout, n, shift, ntiles, counts, digit_base, seg);
         else
-            k4_scatter<false, RANK_BALLOT><<<ntiles, SORT_THREADS, SCATTER_SMEM, st>>>(kin, iin, kout, iout, n, shift, ntiles, t.counts, t.digit_base);
+            k4_scatter<false, RANK_BALLOT, SEG><<<ntiles, SORT_THREADS, SCATTER_SMEM, st>>>(kin, iin, kout, iout, n, shift, ntiles, counts, digit_base, seg);
         }
     }
 
@@ -1260,12 +1432,85 @@ static void pair_passes(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted,
         k4_tile_histogram<SORT_ITEMS><<<ntiles, SORT_THREADS, 0, st>>>(kin, n, shift, ntiles, t.counts);
         k4_row_scan<<<RADIX, 256, 0, st>>>(t.counts, ntiles, t.row_total);
         k4_digit_base<<<1, RADIX, 0, st>>>(t.row_total, t.digit_base);
-        launch_scatter(pi == 0, kin, iin, kout, iout, n, shift, ntiles, t, st);
+        launch_scatter<false>(pi == 0, kin, iin, kout, iout, n, shift, ntiles, t.counts, t.digit_base, SegTables(), st);
         dev_stats().kernel_launches += 4;
         kin = kout;
         iin = iout;
         cur ^= 1;
         }
+    }
+
+// Segmented LSD passes on keys already grouped by the bucket digit (bits >= bshift): only the key
+// bytes below bshift are sorted, inside each bucket; the pass over the bucket digit itself is saved.
+// bucket_base: start of every bucket (the bucket pass's digit_base).  ws: workspace for the tables.
+static size_t seg_tables_bytes(uint64_t n)
+    {
+    const size_t tmax = (size_t)(n / SORT_TILE) + RADIX + 1;
+    return align_up((size_t)RADIX * tmax * 4, 256) + align_up(3 * tmax * 4, 256) + align_up(2 * (RADIX + 1) * 4, 256)
+           + 2 * (size_t)RADIX * RADIX * 4 + 256;
+    }
+
+static int pair_passes_segmented(uint64_t n, const uint32_t* keys_b, uint32_t* keys_sorted, uint32_t* perm_b,
+                                 const KeyPlan& plan, int bshift, const unsigned long long* bucket_base,
+                                 uint32_t* const kbuf[2], uint32_t* const ibuf[2], unsigned char* ws, cudaStream_t st)
+    {
+    const uint32_t tmax = (uint32_t)(n / SORT_TILE) + RADIX + 1;
+    unsigned char* p = ws;
+    uint32_t* counts = (uint32_t*)p;
+    p += align_up((size_t)RADIX * tmax * 4, 256);
+    uint32_t* tile_begin = (uint32_t*)p;
+    uint32_t* tile_cnt = tile_begin + tmax;
+    uint32_t* tile_bkt = tile_cnt + tmax;
+    p += align_up(3 * (size_t)tmax * 4, 256);
+    uint32_t* bstart = (uint32_t*)p;
+    uint32_t* tile_first = bstart + RADIX + 1;
+    p += align_up(2 * (RADIX + 1) * 4, 256);
+    uint32_t* btot = (uint32_t*)p;
+    uint32_t* bbase = btot + RADIX * RADIX;
+    uint32_t* ntiles_dev = bbase + RADIX * RADIX;
+
+    k4s_setup<<<1, RADIX, 0, st>>>(bucket_base, n, bstart, tile_first, tile_begin, tile_cnt, tile_bkt, ntiles_dev);
+    dev_stats().kernel_launches++;
+    SegTables seg;
+    seg.tile_begin = tile_begin;
+    seg.tile_cnt = tile_cnt;
+    seg.tile_bkt = tile_bkt;
+    seg.ntiles = ntiles_dev;
+    seg.bstart = bstart;
+    seg.bbase = bbase;
+    seg.stride = tmax;
+
+    int low[4], nlow = 0;
+    for (int pi = 0; pi < plan.npass; pi++)
+        if (plan.passes[pi] * 8 < bshift)
+            low[nlow++] = plan.passes[pi];
+    const uint32_t* kin = keys_b;
+    const uint32_t* iin = nullptr;
+    int cur = 0;
+    for (int pi = 0; pi < nlow; pi++)
+        {
+        const int shift = low[pi] * 8;
+        const bool last = (pi == nlow - 1);
+        uint32_t* kout = (last && keys_sorted) ? keys_sorted : kbuf[cur];
+        uint32_t* iout = last ? perm_b : ibuf[cur];
+        k4s_histogram<<<tmax, SORT_THREADS, 0, st>>>(kin, shift, seg, counts);
+        k4s_scan<<<RADIX, 256, 0, st>>>(counts, tile_first, tmax, btot);
+        k4s_base<<<RADIX, RADIX, 0, st>>>(btot, bbase);
+        launch_scatter<true>(pi == 0, kin, iin, kout, iout, n, shift, tmax, counts, nullptr, seg, st);
+        dev_stats().kernel_launches += 4;
+        kin = kout;
+        iin = iout;
+        cur ^= 1;
+        }
+    if (nlow == 0)
+        {
+        // nothing varies below the bucket digit: the bucketed order is the sorted order
+        k4_iota<<<dev_sm_count() * 8, 256, 0, st>>>(perm_b, n);
+        dev_stats().kernel_launches++;
+        if (keys_sorted)
+            cudaMemcpyAsync(keys_sorted, keys_b, n * 4, cudaMemcpyDeviceToDevice, st);
+        }
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
     }
 
 static int check_n(uint64_t n)
@@ -1416,7 +1661,7 @@ int dev_reorder_rows(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, ui
         // ---- fast path: interleaved bucketed copy
         const size_t aos_bytes = align_up((size_t)n * row_words * 4, 256);
         void* rws = nullptr;
-        if ((rc = ws_reserve(g_rows_ws, 2 * arr + aos_bytes, &rws)) != 0)
+        if ((rc = ws_reserve(g_rows_ws, 2 * arr + aos_bytes + seg_tables_bytes(n), &rws)) != 0)
             return rc;
         unsigned char* rp = (unsigned char*)rws;
         uint32_t* keys_b = (uint32_t*)rp;
@@ -1479,7 +1724,19 @@ int dev_reorder_rows(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, ui
             return -1;
             }
         phase_mark(2, st);
-        pair_passes(n, keys_b, keys_sorted, perm_b, plan, kbuf, ibuf, t, st);
+        const char* sg = getenv("PGSD_B200_SEGMENTED");
+        if (!(sg && sg[0] == '0'))
+            {
+            // the bucket starts are in t.digit_base (left there by the bucket pass)
+            if (pair_passes_segmented(n, keys_b, keys_sorted, perm_b, plan, bshift, t.digit_base, kbuf, ibuf,
+                                      rp + 2 * arr + aos_bytes, st) != 0)
+                {
+                set_last_error(std::string("reorder segmented passes: ") + cudaGetErrorString(cudaGetLastError()));
+                return -1;
+                }
+            }
+        else
+            pair_passes(n, keys_b, keys_sorted, perm_b, plan, kbuf, ibuf, t, st);
         phase_mark(3, st);
         const uint64_t blocks = (n + GA_ROWS_PER_CTA - 1) / GA_ROWS_PER_CTA;
         const size_t gsm = (size_t)GA_ROWS_PER_CTA * row_words * 4;
