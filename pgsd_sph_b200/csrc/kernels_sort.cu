@@ -522,17 +522,35 @@ __global__ void __launch_bounds__(SORT_THREADS)
         }
     }
 
-// CTA d = digit d; warp w scans the tiles of buckets w, w+8, ... (exclusive, in place) and records
-// the bucket's total for the digit
+// CTA d = digit d: exclusive scan of the digit's tile counts inside every bucket (in place) and the
+// bucket totals.  Buckets of <= 32 tiles (the normal case: 8 tiles per bucket for 16 Mi dense ids) are
+// walked by one thread each, all 256 at once; larger ones by a whole warp, 32 tiles per step.
 __global__ void __launch_bounds__(256)
     k4s_scan(uint32_t* __restrict__ counts, const uint32_t* __restrict__ tile_first, uint32_t stride,
              uint32_t* __restrict__ btot)
     {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     uint32_t* row = counts + (size_t)blockIdx.x * stride;
+        {
+        const int b = threadIdx.x;
+        const uint32_t t0 = tile_first[b], t1 = tile_first[b + 1];
+        if (t1 - t0 <= 32)
+            {
+            uint32_t acc = 0;
+            for (uint32_t i = t0; i < t1; i++)
+                {
+                const uint32_t v = row[i];
+                row[i] = acc;
+                acc += v;
+                }
+            btot[b * RADIX + blockIdx.x] = acc;
+            }
+        }
     for (int b = w; b < RADIX; b += 8)
         {
         const uint32_t t0 = tile_first[b], t1 = tile_first[b + 1];
+        if (t1 - t0 <= 32)
+            continue;
         uint32_t carry = 0;
         for (uint32_t s = t0; s < t1; s += 32)
             {

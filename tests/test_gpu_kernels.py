@@ -264,6 +264,10 @@ def bucket_key_cases():
     yield "all_equal", np.full(5000, 9, dtype=np.uint32)
     yield "tile_edges", rng.permutation(4096 * 5).astype(np.uint32)
     yield "skewed", np.minimum(rng.geometric(0.001, size=150000), 2 ** 20).astype(np.uint32)
+    # one bucket of ~49 tiles (warp-cooperative segment scan) next to nearly empty ones
+    yield "one_big_bucket", np.concatenate([rng.integers(0, 65536, size=400000), (1 << 23) + np.arange(100),
+                                            (1 << 22) + rng.integers(0, 5, size=9000)]).astype(np.uint32)
+    yield "empty_low_bits", (rng.integers(0, 300, size=60000) << 20).astype(np.uint32)   # nothing varies below the bucket digit
 
 
 @pytest.mark.parametrize("rank_mode", ["ballot", "match"])
