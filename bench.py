@@ -340,7 +340,7 @@ def run_read_leg(lib, dist, args, peaks, windows):
     kernels = {
         "k4_digit_census": kern(phase_ms[0], 4, "keys read once; includes the 8 KB D2H + host sync"),
         "k4_bucket_rows": kern(phase_ms[1], 4 + 2 * 40, "tile histogram (4 B) + rows moved once: 40 B read + 40 B written"),
-        "k4_pair_passes": kern(phase_ms[2], 3 * 4 + (4 + 8) + 2 * 16, "3 LSD passes: histogram 4 B each; (key,idx) 12/16/16 B"),
+        "k4_pair_passes": kern(phase_ms[2], 2 * 4 + (4 + 8) + 16, "2 segmented LSD passes inside buckets: histogram 4 B each; (key,idx) 12 + 16 B"),
         "k5_gather": kern(phase_ms[3], 4 + 2 * 36, "perm 4 B + 36 B payload read + 36 B written"),
     }
     reorder_s = dev_ms * 1e-3 / args.steps
