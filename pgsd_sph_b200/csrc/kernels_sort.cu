@@ -125,12 +125,12 @@ __global__ void __launch_bounds__(SORT_THREADS) k4_tile_histogram(const uint32_t
     {
     constexpr int SORT_ITEMS = ITEMS;             // shadows the pair-pass constants on purpose:
     constexpr int SORT_TILE = SORT_THREADS * ITEMS; // the tile must match the scatter kernel's
-    __shared__ unsigned int h[SORT_WARPS / 4][RADIX]; // 4 sub-histograms to thin out contention
-    for (int i = threadIdx.x; i < (SORT_WARPS / 4) * RADIX; i += SORT_THREADS)
+    __shared__ unsigned int h[SORT_WARPS][RADIX]; // one sub-histogram per warp: atomics contend only inside a warp
+    for (int i = threadIdx.x; i < SORT_WARPS * RADIX; i += SORT_THREADS)
         (&h[0][0])[i] = 0;
     __syncthreads();
     const uint64_t base = (uint64_t)blockIdx.x * SORT_TILE;
-    unsigned int* mine = h[(threadIdx.x >> 5) & (SORT_WARPS / 4 - 1)];
+    unsigned int* mine = h[threadIdx.x >> 5];
     if (ITEMS >= 4 && base + SORT_TILE <= n)
         {
         const uint4* k4 = reinterpret_cast<const uint4*>(keys + base);
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k4_tile_histogram(const uint32_t
         {
         unsigned int c = 0;
 #pragma unroll
-        for (int s = 0; s < SORT_WARPS / 4; s++)
+        for (int s = 0; s < SORT_WARPS; s++)
             c += h[s][d];
         counts[(size_t)d * ntiles + blockIdx.x] = c;
         }
@@ -168,6 +168,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k4_tile_histogram(const uint32_t
 __global__ void __launch_bounds__(256) k4_row_scan(uint32_t* __restrict__ counts, uint32_t ntiles,
                                                    unsigned long long* __restrict__ row_total)
     {
+    constexpr int PER = 8; // tiles per thread: 2048 tiles per block-wide step
     __shared__ uint32_t warp_sum[8];
     __shared__ uint32_t carry_s;
     uint32_t* row = counts + (size_t)blockIdx.x * ntiles;
@@ -175,11 +176,17 @@ __global__ void __launch_bounds__(256) k4_row_scan(uint32_t* __restrict__ counts
     if (threadIdx.x == 0)
         carry_s = 0;
     __syncthreads();
-    for (uint32_t start = 0; start < ntiles; start += 256)
+    for (uint32_t start = 0; start < ntiles; start += 256 * PER)
         {
-        uint32_t i = start + threadIdx.x;
-        uint32_t v = i < ntiles ? row[i] : 0;
-        uint32_t x = v;
+        const uint32_t i0 = start + threadIdx.x * PER;
+        uint32_t v[PER], sum = 0;
+#pragma unroll
+        for (int k = 0; k < PER; k++)
+            {
+            v[k] = i0 + k < ntiles ? row[i0 + k] : 0u;
+            sum += v[k];
+            }
+        uint32_t x = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1)
             {
@@ -193,9 +200,15 @@ __global__ void __launch_bounds__(256) k4_row_scan(uint32_t* __restrict__ counts
         uint32_t wbase = 0;
         for (int j = 0; j < w; j++)
             wbase += warp_sum[j];
-        uint32_t carry = carry_s;
-        if (i < ntiles)
-            row[i] = carry + wbase + x - v;
+        const uint32_t carry = carry_s;
+        uint32_t acc = carry + wbase + x - sum;
+#pragma unroll
+        for (int k = 0; k < PER; k++)
+            {
+            if (i0 + k < ntiles)
+                row[i0 + k] = acc;
+            acc += v[k];
+            }
         __syncthreads();
         if (threadIdx.x == 255)
             carry_s = carry + wbase + x;
@@ -494,12 +507,12 @@ __global__ void __launch_bounds__(SORT_THREADS)
     {
     if (blockIdx.x >= seg.ntiles[0])
         return;
-    __shared__ unsigned int h[SORT_WARPS / 4][RADIX];
-    for (int i = threadIdx.x; i < (SORT_WARPS / 4) * RADIX; i += SORT_THREADS)
+    __shared__ unsigned int h[SORT_WARPS][RADIX];
+    for (int i = threadIdx.x; i < SORT_WARPS * RADIX; i += SORT_THREADS)
         (&h[0][0])[i] = 0;
     __syncthreads();
     const uint32_t base = seg.tile_begin[blockIdx.x], cnt = seg.tile_cnt[blockIdx.x];
-    unsigned int* mine = h[(threadIdx.x >> 5) & (SORT_WARPS / 4 - 1)];
+    unsigned int* mine = h[threadIdx.x >> 5];
     uint32_t v[SORT_ITEMS];
 #pragma unroll
     for (int k = 0; k < SORT_ITEMS; k++)
@@ -516,7 +529,7 @@ __global__ void __launch_bounds__(SORT_THREADS)
         {
         unsigned int c = 0;
 #pragma unroll
-        for (int q = 0; q < SORT_WARPS / 4; q++)
+        for (int q = 0; q < SORT_WARPS; q++)
             c += h[q][d];
         counts[(size_t)d * seg.stride + blockIdx.x] = c;
         }
