@@ -182,3 +182,46 @@ def test_vtu_columns_on_device_match_numpy(golden):
             assert c.to_numpy().tobytes() == np.ascontiguousarray(pos[:, j], dtype=np.float64).tobytes()
         assert pd['velocity'][1].to_numpy().tobytes() == np.ascontiguousarray(vel[:, 1], dtype=np.float64).tobytes()
         assert pd['density'].to_numpy().tobytes() == fr.particles.density.to_numpy().astype(np.float64).tobytes()
+
+
+def test_torch_cuda_tensors_cai_and_dlpack(tmp_path):
+    """`data` may be any CUDA array: torch tensors through __cuda_array_interface__, a DLPack-only
+    wrapper through __dlpack__, a strided torch view through the device-side pack (K1)."""
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.skip("torch sees no CUDA device")
+    n = 4097
+    g = torch.Generator(device="cuda").manual_seed(3)
+    pos4 = torch.rand((n, 4), device="cuda", generator=g, dtype=torch.float32)      # HOOMD Scalar4-like
+    dens = torch.rand(n, device="cuda", generator=g, dtype=torch.float64)
+    ids = torch.randperm(n, device="cuda", generator=g).to(torch.int32)
+
+    class DLPackOnly:  # hides __cuda_array_interface__
+        def __init__(self, t):
+            self.t = t
+
+        def __dlpack__(self, stream=None):
+            return self.t.__dlpack__()
+
+        def __dlpack_device__(self):
+            return self.t.__dlpack_device__()
+
+    torch.cuda.synchronize()
+    p = str(tmp_path / "torch.gsd")
+    with fl.open(p, 'w', 'app', 'hoomd', [1, 4]) as f:
+        f.write_chunk("particles/position", pos4[:, :3])                      # strided (n,3) view of (n,4)
+        f.write_chunk("particles/density", DLPackOnly(dens))                  # DLPack intake
+        f.write_chunk("log/particles/id", ids)                                # CAI intake, contiguous
+        f.write_chunk_soa("particles/velocity", [pos4[:, 3], pos4[:, 0], pos4[:, 1]], dtype=np.float64)  # cast f32->f64
+        f.end_frame()
+    with fl.open(p, 'r') as f:
+        h = pos4.cpu().numpy()
+        assert f.read_chunk(0, "particles/position").tobytes() == np.ascontiguousarray(h[:, :3]).tobytes()
+        assert f.read_chunk(0, "particles/density").tobytes() == dens.cpu().numpy().tobytes()
+        assert f.read_chunk(0, "log/particles/id").tobytes() == ids.cpu().numpy().tobytes()
+        want = np.ascontiguousarray(np.stack([h[:, 3], h[:, 0], h[:, 1]], 1), dtype=np.float64)
+        assert f.read_chunk(0, "particles/velocity").tobytes() == want.tobytes()
+        # and back into torch without a copy: DeviceArray exposes __cuda_array_interface__
+        d = f.read_chunk(0, "particles/position", device=True)
+        t = torch.as_tensor(d, device="cuda")
+        assert torch.equal(t, pos4[:, :3])
