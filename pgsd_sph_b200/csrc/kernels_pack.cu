@@ -27,7 +27,8 @@ enum PackKind : int
     KIND_GENERIC = 0, // any types / strides, scalar, coalesced on dst
     KIND_W4 = 1,      // 4-byte elements moved as bits, unit strides, 16-B aligned, M <= 4
     KIND_F64_F32 = 2, // float64 columns -> float32 chunk, unit strides, aligned, M <= 4
-    KIND_COPY = 3     // M == 1 bit copy of 16-B aligned data: plain vector copy over bytes
+    KIND_COPY = 3,    // M == 1 bit copy of 16-B aligned data: plain vector copy over bytes
+    KIND_AOS4 = 4     // M <= 4 leading components of 16-byte records (HOOMD Scalar4 / int4 arrays), 4-byte elements
     };
 
 struct PackSegDev
@@ -102,6 +103,33 @@ template <int M> __device__ __forceinline__ void pack_w4_rows(const PackSegDev& 
         v[j][1] = c.y;
         v[j][2] = c.z;
         v[j][3] = c.w;
+        }
+    unsigned int* out = reinterpret_cast<unsigned int*>(s.dst) + r * M;
+#pragma unroll
+    for (int q = 0; q < M; q++)
+        {
+        uint4 o;
+        o.x = v[(4 * q + 0) % M][(4 * q + 0) / M];
+        o.y = v[(4 * q + 1) % M][(4 * q + 1) / M];
+        o.z = v[(4 * q + 2) % M][(4 * q + 2) / M];
+        o.w = v[(4 * q + 3) % M][(4 * q + 3) / M];
+        stg_v4(out + 4 * q, o);
+        }
+    }
+
+// rows r..r+3 of an array of 16-byte records: component j of record i -> dst[(r+i)*M + j]
+template <int M> __device__ __forceinline__ void pack_aos4_rows(const PackSegDev& s, unsigned long long r)
+    {
+    const uint4* in = reinterpret_cast<const uint4*>(s.base[0]) + r;
+    unsigned int v[4][4]; // v[j][i]
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        {
+        uint4 a = ldg_stream_v4(in + i);
+        v[0][i] = a.x;
+        v[1][i] = a.y;
+        v[2][i] = a.z;
+        v[3][i] = a.w;
         }
     unsigned int* out = reinterpret_cast<unsigned int*>(s.dst) + r * M;
 #pragma unroll
@@ -237,7 +265,7 @@ __global__ void __launch_bounds__(PACK_THREADS) k1_pack_frame(const __grid_const
                 si = k;
         const PackSegDev& s = args.s[si];
         const unsigned long long row0 = (unsigned long long)(tile - s.tile_begin) * TILE_ROWS;
-        if (s.kind == KIND_W4 || s.kind == KIND_F64_F32)
+        if (s.kind == KIND_W4 || s.kind == KIND_F64_F32 || s.kind == KIND_AOS4)
             {
 #pragma unroll
             for (int it = 0; it < PACK_UNROLL; it++)
@@ -246,7 +274,17 @@ __global__ void __launch_bounds__(PACK_THREADS) k1_pack_frame(const __grid_const
                                        + (unsigned long long)threadIdx.x * ROWS_PER_THREAD;
                 if (r + ROWS_PER_THREAD <= s.N)
                     {
-                    if (s.kind == KIND_W4)
+                    if (s.kind == KIND_AOS4)
+                        {
+                        switch (s.M)
+                            {
+                            case 1: pack_aos4_rows<1>(s, r); break;
+                            case 2: pack_aos4_rows<2>(s, r); break;
+                            case 3: pack_aos4_rows<3>(s, r); break;
+                            default: pack_aos4_rows<4>(s, r); break;
+                            }
+                        }
+                    else if (s.kind == KIND_W4)
                         {
                         switch (s.M)
                             {
@@ -405,6 +443,15 @@ int pack_launch(const PackSegment* segs, int nsegs, cudaStream_t st)
             s.kind = KIND_W4;
         else if (unit && aligned && g.M <= 4 && g.src_type == T_F64 && g.dst_type == T_F32)
             s.kind = KIND_F64_F32;
+        else if (g.M <= 4 && s.bitcopy && s.elem_size == 4 && (uintptr_t)g.dst % 16 == 0 && (uintptr_t)g.base[0] % 16 == 0)
+            {
+            // components 0..M-1 of 16-byte records: every column is base[0] + 4*j with stride 4
+            bool rec = true;
+            for (unsigned j = 0; j < g.M; j++)
+                rec = rec && g.stride[j] == 4 && (const char*)g.base[j] == (const char*)g.base[0] + 4 * j;
+            if (rec)
+                s.kind = KIND_AOS4;
+            }
         if (tiles + ntiles > 0xffffffffull)
             {
             set_last_error("pack: frame too large for one launch");

@@ -332,3 +332,20 @@ def test_reorder_bucket_layouts_and_row_widths(cuda, monkeypatch, widths, layout
             assert (p == o.astype(np.uint32)).all()
         for f, g in zip(fields, outs):
             assert g.tobytes() == f[o].tobytes()
+
+
+@pytest.mark.parametrize("M", [1, 2, 3, 4])
+@pytest.mark.parametrize("N", [1, 5, 4096, 100003])
+@pytest.mark.parametrize("dt", [np.float32, np.int32])
+def test_pack_scalar4_records(cuda, N, M, dt):
+    """HOOMD Scalar4 / int4 arrays: the leading M components of 16-byte records, read in place
+    (one device buffer, columns base+4j with stride 4) -> (N, M); takes K1's record path."""
+    rng = np.random.default_rng(N + M)
+    aos = (rng.standard_normal((N, 4)) * 1000).astype(dt)
+    d = DeviceArray.from_numpy(aos)
+    cols = (_lib.Column * M)(*[_lib.Column(d.ptr + 4 * j, 4) for j in range(M)])
+    out = DeviceArray((N, M), dt)
+    t = _NP_TO_PGSD[np.dtype(dt)]
+    _lib.check(cuda.pgsd_b200_pack_soa(out.ptr, t, N, M, t, cols, None), "pack_soa")
+    _lib.check(cuda.pgsd_b200_synchronize(), "sync")
+    assert out.to_numpy().tobytes() == np.ascontiguousarray(aos[:, :M]).tobytes()
