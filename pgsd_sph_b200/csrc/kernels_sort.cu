@@ -935,27 +935,25 @@ __global__ void __launch_bounds__(SORT_THREADS, 2)
         }
     if ((RW & 1u) == 0)
         {
-        // rows are 8-byte multiples: one 64-bit store per two columns
+        // rows are 8-byte multiples: one 64-bit store per two columns.  Thread -> (row slot, column
+        // pair) is fixed for the whole loop, so the column descriptors live in registers and
+        // consecutive threads still write consecutive 8-byte pieces of consecutive rows.
         const uint32_t R2 = RW / 2;
-        const uint32_t total2 = tile_n * R2;
-        uint2* out2 = reinterpret_cast<uint2*>(aos_out);
-        uint32_t j = tid / R2, c = tid - j * R2;
-        const uint32_t dj = SORT_THREADS / R2, dc = SORT_THREADS - dj * R2;
-        for (uint32_t q = tid; q < total2; q += SORT_THREADS)
+        const uint32_t rows_per_step = SORT_THREADS / R2;
+        const uint32_t slot = tid / R2, c = tid - slot * R2;
+        if (slot < rows_per_step)
             {
-            const unsigned long long g = sm.gdelta[(skeys[j] >> shift) & 255u] + j;
-            const uint32_t e = sinv[j];
+            uint2* out2 = reinterpret_cast<uint2*>(aos_out);
             const uint32_t c0 = col[2 * c], c1 = col[2 * c + 1];
-            uint2 v;
-            v.x = (c0 & 255u) ? raw[(c0 >> 8) + e * (c0 & 255u)] : (uint32_t)(tile_base + e);
-            v.y = (c1 & 255u) ? raw[(c1 >> 8) + e * (c1 & 255u)] : (uint32_t)(tile_base + e);
-            out2[g * R2 + c] = v;
-            j += dj;
-            c += dc;
-            if (c >= R2)
+            const uint32_t w0 = c0 & 255u, w1 = c1 & 255u, b0 = c0 >> 8, b1 = c1 >> 8;
+            for (uint32_t j = slot; j < tile_n; j += rows_per_step)
                 {
-                c -= R2;
-                j++;
+                const unsigned long long g = sm.gdelta[(skeys[j] >> shift) & 255u] + j;
+                const uint32_t e = sinv[j];
+                uint2 v;
+                v.x = w0 ? raw[b0 + e * w0] : (uint32_t)(tile_base + e);
+                v.y = w1 ? raw[b1 + e * w1] : (uint32_t)(tile_base + e);
+                out2[g * R2 + c] = v;
                 }
             }
         }
