@@ -616,6 +616,7 @@ def main():
     ap.add_argument("--particles", type=int, default=WRITE_PARTICLES)
     ap.add_argument("--read-particles", type=int, default=READ_PARTICLES)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="skip the 14 GB benchmark-write leg (contract tests)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     ncores = os.cpu_count() or 1
@@ -639,7 +640,7 @@ def main():
         w = cpu_write_reference(n_w, steps_ref, nr, warm=warm)
         n_r = min(args.read_particles, 2 * 1024 * 1024)
         r = cpu_read_reference(n_r, min(args.steps, 4), warm=1)
-        bw = cpu_benchmark_write_reference(min(ncores, 8))
+        bw = None if args.quick else cpu_benchmark_write_reference(min(ncores, 8))
         if w is None:
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_driver is not built"}))
             return 0
@@ -681,7 +682,7 @@ def main():
         from pgsd_sph_b200 import comm
         comm.init_nccl(dist.rank, dist.world, dist.bcast_bytes, dist.local)
     wr = run_write_leg(lib, dist, args, peaks, windows)
-    bw = run_benchmark_write_leg(lib, dist, args)
+    bw = None if args.quick else run_benchmark_write_leg(lib, dist, args)
     sampler.stop()
 
     line = None
