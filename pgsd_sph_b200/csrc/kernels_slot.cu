@@ -1,0 +1,816 @@
+// kernels_slot.cu -- K4/K5 "slot path": the reorder of a decoded frame when the particle ids are UNIQUE
+// (the normal case: ids are a permutation of 0..N-1; hoomd.py:885-893 reads them
+// from log/particles/id).
+//
+// Same oracle as kernels_sort.cu:  o = numpy.argsort(ids, kind='stable');  out_f = in_f[o].
+// With unique keys the stable order is simply the key order, so no ranking is needed at all:
+//
+//   k6_slot_hist     histogram of the key bits above the low L ("slot") bits: <= 32768 buckets of at most
+//                    CAP = 2^L keys each.  A bucket with more than CAP keys proves a duplicate -> flag.
+//   k6_slot_scan     exclusive scan of the bucket counts (one CTA) -> bucket bases and write cursors.
+//   k6_slot_scatter  rows (key + all fields [+ original index]) are staged SoA -> shared memory with one
+//                    TMA bulk copy per field, every row takes the next free position of its bucket
+//                    (one global atomic per row), and leaves as one interleaved record.  Buckets are
+//                    contiguous in the interleaved copy, in key order.
+//   k6_slot_place    one CTA per bucket: the bucket (<= CAP rows, 40 KB for the SPH schema) comes in with
+//                    ONE TMA bulk copy, every row is placed at slot = key & (CAP-1) (an occupancy bitmap
+//                    detects duplicates and compacts gaps), and the fields are written back SoA, fully
+//                    coalesced, at the bucket's own output range.
+//
+// Bytes moved: 4 (hist) + 40 + 40 (scatter) + 40 + 40 (place) = 164 B/particle for the 40-byte SPH row,
+// against 200 B/particle of the general path (bucket pass + 2 segmented pair passes + gather), and none
+// of its ballot ranking.  When a duplicate key is found (flag), nothing of the result is trusted: the
+// caller falls back to the stable general path of kernels_sort.cu.
+//
+// sm_100a only (cp.async.bulk + mbarrier).  No CPU fallback.
+#include "device_internal.h"
+
+#include <cstdlib>
+
+namespace pgsdb
+{
+namespace
+    {
+constexpr int SLOT_MAX_FIELDS = 18;    // key + 16 caller fields + original index
+constexpr int SLOT_MAX_ROW_WORDS = 32; // one warp store covers >= 1 row
+constexpr int SLOT_MIN_BITS = 10;
+constexpr int SLOT_MAX_BITS = 12;
+constexpr int SLOT_MAX_BUCKET_BITS = 15; // 32768 buckets: 128 KB histogram in shared memory
+
+struct SlotField
+    {
+    const uint32_t* in; // n rows of `words` words; NULL: the row's original index
+    uint32_t* out;      // destination of the reordered field; NULL: not wanted
+    uint32_t words;
+    uint32_t off;       // word offset inside the interleaved row
+    };
+struct SlotArgs
+    {
+    SlotField f[SLOT_MAX_FIELDS];
+    int nfields;
+    uint32_t row_words;
+    int bulk; // every input is 16-byte aligned: full tiles are staged with cp.async.bulk
+    uint32_t nbl; // 0: buckets are contiguous in the interleaved copy ("flat").  nb: "lines" layout -- 128-byte line j of
+                  // bucket b lives at line j * nb + b, so that the lines the buckets are currently filling (about the
+                  // same j for all of them) form one compact, advancing window instead of nb windows spread over the
+                  // whole copy: the L2 write-backs then fall into few open DRAM rows
+    int debug; // timing experiments only (results are wrong): 1 = no atomics, identity positions; 2 = atomics, identity
+               // positions; 3 = atomics, nothing written; 4 = staging only
+    };
+
+// ---- PTX wrappers: mbarrier + 1-D bulk copy global -> shared (TMA engine) ---------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p)
+    {
+    return (uint32_t)__cvta_generic_to_shared(p);
+    }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+    {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+    {
+    unsigned long long state;
+    asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 %0, [%1], %2;"
+                 : "=l"(state)
+                 : "r"(bar), "r"(bytes)
+                 : "memory");
+    (void)state;
+    }
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+    {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+    }
+// Waits for phase `parity`; gives up after ~2 s worth of cycles so that a lost copy cannot hang the GPU.
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity)
+    {
+    const long long t0 = clock64();
+    for (;;)
+        {
+        uint32_t done;
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
+        if (done)
+            return true;
+        if (clock64() - t0 > 4000000000ll)
+            return false;
+        }
+    }
+
+// flag words (device): [0] set by k6_slot_scan: a bucket holds more than CAP keys (duplicate ids)
+//                      [1] set by k6_slot_place: 1 = two rows of a bucket share a slot (duplicate ids),
+//                          3 = a bulk copy never arrived
+// ---- bucket histogram ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k6_slot_hist(const uint32_t* __restrict__ keys, uint64_t n, int L, uint32_t bmask,
+                                                    uint32_t nb, uint32_t* __restrict__ counts)
+    {
+    extern __shared__ uint32_t hist[];
+    for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x)
+        hist[i] = 0;
+    __syncthreads();
+    const uint64_t n4 = n / 4;
+    const uint4* k4 = reinterpret_cast<const uint4*>(keys);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (uint64_t)gridDim.x * blockDim.x)
+        {
+        const uint4 v = __ldg(k4 + i);
+        atomicAdd(&hist[(v.x >> L) & bmask], 1u);
+        atomicAdd(&hist[(v.y >> L) & bmask], 1u);
+        atomicAdd(&hist[(v.z >> L) & bmask], 1u);
+        atomicAdd(&hist[(v.w >> L) & bmask], 1u);
+        }
+    if (blockIdx.x == 0)
+        for (uint64_t i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x)
+            atomicAdd(&hist[(keys[i] >> L) & bmask], 1u);
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x)
+        {
+        const uint32_t c = hist[i];
+        if (c)
+            atomicAdd(counts + i, c);
+        }
+    }
+
+// ---- exclusive scan of <= 32768 bucket counts, one CTA ---------------------------------------------------
+// Thread t owns the `per` consecutive buckets from t * per; its counts are fetched with independent loads
+// (one memory latency for the whole table) and kept in registers for the second sweep.
+constexpr int SCAN_MAX_PER = (1 << SLOT_MAX_BUCKET_BITS) / 1024;
+__global__ void __launch_bounds__(1024) k6_slot_scan(const uint32_t* __restrict__ counts, uint32_t nb, uint32_t cap,
+                                                    uint32_t n, uint32_t* __restrict__ base, uint32_t* __restrict__ cursor,
+                                                    uint32_t cstride, int zero_cursors, uint32_t* __restrict__ flag)
+    {
+    __shared__ uint32_t wsum[32];
+    __shared__ uint32_t over;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const uint32_t per = (nb + 1023u) / 1024u;
+    const uint32_t b0 = (uint32_t)tid * per;
+    uint32_t c[SCAN_MAX_PER];
+#pragma unroll
+    for (int i = 0; i < SCAN_MAX_PER; i++)
+        c[i] = ((uint32_t)i < per && b0 + i < nb) ? __ldg(counts + b0 + i) : 0u;
+    uint32_t s = 0, mx = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_MAX_PER; i++)
+        {
+        s += c[i];
+        mx = c[i] > mx ? c[i] : mx;
+        }
+    uint32_t inc = s;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+        {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d)
+            inc += t;
+        }
+    if (lane == 31)
+        wsum[w] = inc;
+    if (tid == 0)
+        over = 0;
+    __syncthreads();
+    if (w == 0)
+        {
+        const uint32_t v = wsum[lane];
+        uint32_t iv = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+            {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, iv, d);
+            if (lane >= d)
+                iv += t;
+            }
+        wsum[lane] = iv - v;
+        }
+    __syncthreads();
+    if (mx > cap)
+        over = 1;
+    uint32_t run = wsum[w] + inc - s;
+#pragma unroll
+    for (int i = 0; i < SCAN_MAX_PER; i++)
+        if ((uint32_t)i < per && b0 + i < nb)
+            {
+            base[b0 + i] = run;
+            cursor[(size_t)(b0 + i) * cstride] = zero_cursors ? 0u : run;
+            run += c[i];
+            }
+    if (tid == 0)
+        base[nb] = n;
+    __syncthreads();
+    if (tid == 0 && over)
+        flag[0] = 1;
+    }
+
+// ---- scatter: every row to the next free position of its bucket, as one interleaved record -------------
+// Field tiles sit field-major in shared memory, tile i shifted by 4 * i words so that the columns of one
+// record fall into different banks.  The keys (field 0) are loaded straight into registers: their atomics
+// are in flight while the TMA engine brings the payload tiles.
+constexpr uint32_t SLOT_SKEW = 4; // words; keeps every tile 16-byte aligned for the bulk copies
+
+template <int T, int NT>
+__global__ void __launch_bounds__(NT) k6_slot_scatter(uint64_t n, int L, uint32_t bmask, uint32_t* __restrict__ cursor,
+                                                     uint32_t cstride, uint32_t* __restrict__ aos, uint32_t* __restrict__ flag,
+                                                     const __grid_constant__ SlotArgs args)
+    {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long bar_mem;
+    __shared__ uint32_t col[SLOT_MAX_ROW_WORDS]; // column c of the record: (word offset of its field tile + c') << 8 | W; 0: original index
+    uint32_t* raw = reinterpret_cast<uint32_t*>(smem_raw); // field tiles: T * W words each (+ skew)
+    if (flag[0] != 0) // written by k6_slot_scan only: uniform
+        return;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const uint64_t tile0 = (uint64_t)blockIdx.x * T;
+    const uint32_t tile_n = (uint32_t)((n - tile0) < (uint64_t)T ? (n - tile0) : T);
+    const uint32_t RW = args.row_words;
+    constexpr int PER = T / NT;
+
+    // keys of my rows: registers
+    uint32_t key[PER];
+#pragma unroll
+    for (int k = 0; k < PER; k++)
+        {
+        const uint32_t r = (uint32_t)tid + (uint32_t)k * NT;
+        key[k] = r < tile_n ? __ldg(args.f[0].in + tile0 + r) : 0u;
+        }
+
+    uint32_t fbase = 0, tx_bytes = 0;
+    for (int fi = 0; fi < args.nfields; fi++)
+        {
+        const uint32_t W = args.f[fi].words;
+        const bool real = args.f[fi].in != nullptr;
+        if (tid < (int)W)
+            col[args.f[fi].off + tid] = real ? (((fbase + (uint32_t)tid) << 8) | W) : 0u;
+        if (real)
+            {
+            fbase += (uint32_t)T * W + SLOT_SKEW;
+            if (fi > 0)
+                tx_bytes += (uint32_t)T * W * 4u;
+            }
+        }
+    uint32_t* sdst = raw + fbase; // T : row -> record position in the interleaved copy
+
+    // (1) the payload tiles start their way global -> shared
+    const bool bulk = args.bulk && tile_n == (uint32_t)T && tx_bytes != 0;
+    const uint32_t bar = smem_u32(&bar_mem);
+    if (bulk && tid == 0)
+        mbar_init(bar, 1);
+    __syncthreads();
+    if (bulk)
+        {
+        if (tid == 0)
+            {
+            mbar_expect_tx(bar, tx_bytes);
+            uint32_t fb = (uint32_t)T + SLOT_SKEW;
+            for (int fi = 1; fi < args.nfields; fi++)
+                {
+                const uint32_t W = args.f[fi].words;
+                if (args.f[fi].in == nullptr)
+                    continue;
+                bulk_g2s(smem_u32(raw + fb), args.f[fi].in + tile0 * W, (uint32_t)T * W * 4u, bar);
+                fb += (uint32_t)T * W + SLOT_SKEW;
+                }
+            }
+        }
+    else
+        {
+        uint32_t fb = (uint32_t)T + SLOT_SKEW;
+        for (int fi = 1; fi < args.nfields; fi++)
+            {
+            const uint32_t W = args.f[fi].words;
+            if (args.f[fi].in == nullptr)
+                continue;
+            const uint32_t* in = args.f[fi].in + tile0 * W;
+            const uint32_t total = tile_n * W;
+            for (uint32_t q = tid; q < total; q += NT)
+                raw[fb + q] = __ldg(in + q);
+            fb += (uint32_t)T * W + SLOT_SKEW;
+            }
+        }
+
+    // (2) one position per row from the bucket's cursor
+    uint32_t d[PER];
+#pragma unroll
+    for (int k = 0; k < PER; k++)
+        {
+        const uint32_t r = (uint32_t)tid + (uint32_t)k * NT;
+        d[k] = 0;
+        if (r < tile_n)
+            {
+            if (args.debug == 1 || args.debug == 4)
+                d[k] = (uint32_t)(tile0 + r);
+            else
+                {
+                const uint32_t b = (key[k] >> L) & bmask;
+                d[k] = atomicAdd(cursor + (size_t)b * cstride, 1u);
+                if (args.nbl)
+                    d[k] |= b << 12; // position inside the bucket (< 4096) and the bucket
+                if (args.debug == 2 || args.debug == 3)
+                    d[k] = (uint32_t)(tile0 + r) + (d[k] >> 31);
+                }
+            }
+        }
+#pragma unroll
+    for (int k = 0; k < PER; k++)
+        {
+        const uint32_t r = (uint32_t)tid + (uint32_t)k * NT;
+        sdst[r] = d[k];
+        raw[r] = key[k];
+        }
+    if (bulk)
+        {
+        const bool ok = mbar_wait(bar, 0);
+        if (__syncthreads_or(!ok))
+            {
+            if (tid == 0)
+                flag[1] = 3;
+            return;
+            }
+        }
+    else
+        __syncthreads();
+
+    if (args.debug >= 3) // timing experiments: no records written
+        {
+        if (sdst[tid] == 0xffffffffu)
+            aos[tid] = raw[tid];
+        return;
+        }
+    // (3) records out: a group of lanes writes one record (consecutive words), G records per warp store
+    constexpr uint32_t NW = NT / 32;
+    constexpr int U = 4;
+    if ((RW & 1u) == 0)
+        {
+        const uint32_t R2 = RW / 2, G = 32u / R2;
+        const uint32_t g = (uint32_t)lane / R2, c2 = (uint32_t)lane - g * R2;
+        if (g < G)
+            {
+            const uint32_t ca = col[2 * c2], cb = col[2 * c2 + 1];
+            const uint32_t Wa = ca & 255u, fa = ca >> 8, Wb = cb & 255u, fb = cb >> 8;
+            uint2* aos2 = reinterpret_cast<uint2*>(aos);
+            const uint32_t step = NW * G;
+            for (uint32_t r0 = (uint32_t)w * G + g; r0 < tile_n; r0 += step * U)
+                {
+                uint32_t dd[U];
+                uint2 v[U];
+#pragma unroll
+                for (int u = 0; u < U; u++)
+                    {
+                    const uint32_t r = r0 + (uint32_t)u * step;
+                    if (r < tile_n)
+                        {
+                        dd[u] = sdst[r];
+                        v[u].x = Wa ? raw[fa + r * Wa] : (uint32_t)(tile0 + r);
+                        v[u].y = Wb ? raw[fb + r * Wb] : (uint32_t)(tile0 + r);
+                        }
+                    }
+#pragma unroll
+                for (int u = 0; u < U; u++)
+                    if (r0 + (uint32_t)u * step < tile_n)
+                        {
+                        if (args.nbl)
+                            {
+                            const uint32_t o = (dd[u] & 4095u) * (RW * 4u) + c2 * 8u;
+                            const uint64_t at = ((uint64_t)((o >> 7) * args.nbl + (dd[u] >> 12)) << 7) + (o & 127u);
+                            *reinterpret_cast<uint2*>(reinterpret_cast<unsigned char*>(aos) + at) = v[u];
+                            }
+                        else
+                            aos2[(uint64_t)dd[u] * R2 + c2] = v[u];
+                        }
+                }
+            }
+        }
+    else
+        {
+        const uint32_t G = 32u / RW;
+        const uint32_t g = (uint32_t)lane / RW, c = (uint32_t)lane - g * RW;
+        if (g < G)
+            {
+            const uint32_t cc = col[c];
+            const uint32_t W = cc & 255u, fb = cc >> 8;
+            const uint32_t step = NW * G;
+            for (uint32_t r0 = (uint32_t)w * G + g; r0 < tile_n; r0 += step * U)
+                {
+                uint32_t dd[U], v[U];
+#pragma unroll
+                for (int u = 0; u < U; u++)
+                    {
+                    const uint32_t r = r0 + (uint32_t)u * step;
+                    if (r < tile_n)
+                        {
+                        dd[u] = sdst[r];
+                        v[u] = W ? raw[fb + r * W] : (uint32_t)(tile0 + r);
+                        }
+                    }
+#pragma unroll
+                for (int u = 0; u < U; u++)
+                    if (r0 + (uint32_t)u * step < tile_n)
+                        {
+                        if (args.nbl)
+                            {
+                            const uint32_t o = (dd[u] & 4095u) * (RW * 4u) + c * 4u;
+                            const uint64_t at = ((uint64_t)((o >> 7) * args.nbl + (dd[u] >> 12)) << 7) + (o & 127u);
+                            *reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(aos) + at) = v[u];
+                            }
+                        else
+                            aos[(uint64_t)dd[u] * RW + c] = v[u];
+                        }
+                }
+            }
+        }
+    }
+
+// ---- place: one CTA per bucket; slot = key & (CAP-1) is the row's rank among the bucket's (unique) keys ---
+template <int W>
+__device__ __forceinline__ void slot_emit(uint32_t* __restrict__ out, const uint32_t* __restrict__ src,
+                                          const uint16_t* __restrict__ row_at, uint32_t total, uint32_t RW, int tid, int nt)
+    {
+    for (uint32_t q = tid; q < total; q += nt)
+        {
+        const uint32_t j = q / W, c = q - j * W;
+        out[q] = src[(uint32_t)row_at[j] * RW + c];
+        }
+    }
+
+__global__ void __launch_bounds__(1024) k6_slot_place(const uint32_t* __restrict__ base, int L, const uint32_t* __restrict__ aos,
+                                                     uint32_t* __restrict__ flag, const __grid_constant__ SlotArgs args)
+    {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long bar_mem;
+    if (flag[0] != 0) // written by k6_slot_scan only: uniform
+        return;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nt = blockDim.x;
+    const uint32_t r0 = base[blockIdx.x];
+    const uint32_t cnt = base[blockIdx.x + 1] - r0;
+    if (cnt == 0)
+        return;
+    const uint32_t CAP = 1u << L, RW = args.row_words, nwords = CAP / 32;
+    // shared memory: [records: CAP*RW words + 32 B][row_of u16 CAP][row_at u16 CAP][bitmap nwords][wpref nwords]
+    const uint64_t byte0 = args.nbl ? 0ull : (uint64_t)r0 * RW * 4u;
+    const uint32_t lead = (uint32_t)(byte0 & 15u);
+    const uint32_t* rows = reinterpret_cast<const uint32_t*>(smem_raw + lead);
+    unsigned char* p = smem_raw + (size_t)CAP * RW * 4 + 128;
+    uint16_t* row_of = reinterpret_cast<uint16_t*>(p);
+    uint16_t* row_at2 = row_of + CAP;
+    uint32_t* bitmap = reinterpret_cast<uint32_t*>(row_at2 + CAP);
+    uint32_t* wpref = bitmap + nwords;
+
+    // (1) the whole bucket with one bulk copy (source start rounded down, size rounded up to 16 bytes)
+    const uint32_t bar = smem_u32(&bar_mem);
+    if (args.nbl)
+        {
+        // "lines" layout: the bucket's 128-byte lines are nb lines apart; 16-byte cp.async pieces
+        const uint32_t pieces = ((cnt * RW * 4u + 127u) >> 7) * 8u;
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(aos);
+        const uint32_t sbase = smem_u32(smem_raw);
+        for (uint32_t q = tid; q < pieces; q += nt)
+            {
+            const uint64_t at = ((uint64_t)((q >> 3) * args.nbl + blockIdx.x) << 7) + (q & 7u) * 16u;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + q * 16u), "l"(src + at) : "memory");
+            }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        for (uint32_t i = tid; i < nwords; i += nt)
+            bitmap[i] = 0;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        }
+    else if (args.bulk)
+        {
+        if (tid == 0)
+            mbar_init(bar, 1);
+        for (uint32_t i = tid; i < nwords; i += nt)
+            bitmap[i] = 0;
+        __syncthreads();
+        if (tid == 0)
+            {
+            const uint32_t bytes = (lead + cnt * RW * 4u + 15u) & ~15u;
+            mbar_expect_tx(bar, bytes);
+            bulk_g2s(smem_u32(smem_raw), reinterpret_cast<const unsigned char*>(aos) + (byte0 - lead), bytes, bar);
+            }
+        const bool ok = mbar_wait(bar, 0);
+        if (__syncthreads_or(!ok))
+            {
+            if (tid == 0)
+                flag[1] = 3;
+            return;
+            }
+        }
+    else
+        {
+        for (uint32_t i = tid; i < nwords; i += nt)
+            bitmap[i] = 0;
+        uint32_t* dst = reinterpret_cast<uint32_t*>(smem_raw + lead);
+        const uint32_t* src = aos + (uint64_t)r0 * RW;
+        for (uint32_t q = tid; q < cnt * RW; q += nt)
+            dst[q] = __ldg(src + q);
+        __syncthreads();
+        }
+
+    // (2) slot of every row; a slot taken twice is a duplicate key
+    int dup = 0;
+    for (uint32_t r = tid; r < cnt; r += nt)
+        {
+        const uint32_t s = rows[r * RW] & (CAP - 1u);
+        const uint32_t bit = 1u << (s & 31u);
+        if (atomicOr(&bitmap[s >> 5], bit) & bit)
+            dup = 1;
+        row_of[s] = (uint16_t)r;
+        }
+    if (__syncthreads_or(dup))
+        {
+        if (tid == 0)
+            flag[1] = 1;
+        return;
+        }
+
+    // (3) sorted position -> row.  A full bucket has every slot taken: position == slot.
+    const uint16_t* row_at = row_of;
+    if (cnt != CAP)
+        {
+        if (w == 0)
+            {
+            uint32_t run = 0;
+            for (uint32_t i0 = 0; i0 < nwords; i0 += 32)
+                {
+                const uint32_t pc = __popc(bitmap[i0 + lane]); // nwords is a multiple of 32
+                uint32_t inc = pc;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1)
+                    {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+                    if (lane >= d)
+                        inc += t;
+                    }
+                wpref[i0 + lane] = run + inc - pc;
+                run += __shfl_sync(0xffffffffu, inc, 31);
+                }
+            }
+        __syncthreads();
+        for (uint32_t s = tid; s < CAP; s += nt)
+            {
+            const uint32_t wd = bitmap[s >> 5];
+            if ((wd >> (s & 31u)) & 1u)
+                row_at2[wpref[s >> 5] + __popc(wd & ((1u << (s & 31u)) - 1u))] = row_of[s];
+            }
+        __syncthreads();
+        row_at = row_at2;
+        }
+
+    // (4) fields out, SoA, coalesced: the bucket's output rows are [r0, r0 + cnt) of every field
+    for (int fi = 0; fi < args.nfields; fi++)
+        {
+        const SlotField f = args.f[fi];
+        if (f.out == nullptr)
+            continue;
+        const uint32_t W = f.words;
+        uint32_t* out = f.out + (uint64_t)r0 * W;
+        const uint32_t* src = rows + f.off;
+        const uint32_t total = cnt * W;
+        if (W == 1)
+            slot_emit<1>(out, src, row_at, total, RW, tid, nt);
+        else if (W == 3)
+            slot_emit<3>(out, src, row_at, total, RW, tid, nt);
+        else if (W == 2)
+            slot_emit<2>(out, src, row_at, total, RW, tid, nt);
+        else if (W == 4)
+            slot_emit<4>(out, src, row_at, total, RW, tid, nt);
+        else
+            for (uint32_t q = tid; q < total; q += nt)
+                {
+                const uint32_t j = q / W, c = q - j * W;
+                out[q] = src[(uint32_t)row_at[j] * RW + c];
+                }
+        }
+    }
+    } // namespace
+
+// ---- host side -------------------------------------------------------------------------------------------
+static void* g_slot_ws = nullptr;
+static size_t g_slot_ws_bytes = 0;
+static uint32_t* g_slot_flag_host = nullptr; // pinned, 2 words
+
+void slot_release_workspace()
+    {
+    if (g_slot_ws)
+        cudaFree(g_slot_ws);
+    g_slot_ws = nullptr;
+    g_slot_ws_bytes = 0;
+    if (g_slot_flag_host)
+        cudaFreeHost(g_slot_flag_host);
+    g_slot_flag_host = nullptr;
+    }
+
+static inline size_t up256(size_t v) { return (v + 255) / 256 * 256; }
+
+static size_t slot_place_smem(int L, uint32_t rw)
+    {
+    const size_t cap = (size_t)1 << L;
+    return cap * rw * 4 + 128 + 2 * cap * 2 + 2 * (cap / 32) * 4;
+    }
+
+template <int T, int NT>
+static cudaError_t launch_scatter(uint64_t n, int L, uint32_t bmask, uint32_t* cursor, uint32_t cstride, uint32_t* aos, uint32_t* flag,
+                                  const SlotArgs& a, uint32_t in_words, cudaStream_t st)
+    {
+    const size_t smem = ((size_t)in_words + 1) * T * 4 + SLOT_MAX_FIELDS * SLOT_SKEW * 4;
+    static size_t attr = 0;
+    if (smem > attr)
+        {
+        cudaError_t e = cudaFuncSetAttribute(k6_slot_scatter<T, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess)
+            return e;
+        attr = smem;
+        }
+    const uint64_t tiles = (n + T - 1) / T;
+    k6_slot_scatter<T, NT><<<(unsigned)tiles, NT, smem, st>>>(n, L, bmask, cursor, cstride, aos, flag, a);
+    return cudaGetLastError();
+    }
+
+// Tries the slot path.  *done = 1: outputs are complete (stream-ordered work finished; the flag was read
+// back).  *done = 0: not applicable or duplicate keys found -- the caller must run the general path (inputs
+// are untouched).  phase: optional cudaEvent_t[2] recorded after the scatter and after the placement.
+int dev_reorder_slot(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, uint32_t* perm, int nfields,
+                     const ReorderField* fields, int topbit, void* stream_v, int* done, void (*mark)(int, cudaStream_t))
+    {
+    *done = 0;
+    const char* en = getenv("PGSD_B200_SLOT");
+    if (en && en[0] == '0')
+        return 0;
+    if (n == 0 || n >= 0xffffffffull || nfields + 2 > SLOT_MAX_FIELDS || keys_sorted == keys)
+        return 0;
+    cudaStream_t st = (cudaStream_t)stream_v;
+
+    SlotArgs a;
+    memset(&a, 0, sizeof(a));
+    int nf = 0;
+    uint32_t off = 0, in_words = 0;
+    bool aligned = ((uintptr_t)keys & 15u) == 0;
+    if (!aligned)
+        return 0; // the histogram reads the keys as uint4
+    a.f[nf++] = SlotField { keys, keys_sorted, 1u, off };
+    off += 1;
+    in_words += 1;
+    for (int i = 0; i < nfields; i++)
+        {
+        const ReorderField& f = fields[i];
+        if (f.row_bytes == 0 || f.row_bytes % 4 != 0 || (((uintptr_t)f.in | (uintptr_t)f.out) & 3u) != 0 || f.in == nullptr
+            || f.out == nullptr)
+            return 0;
+        if (((uintptr_t)f.in & 15u) != 0)
+            aligned = false;
+        a.f[nf++] = SlotField { (const uint32_t*)f.in, (uint32_t*)f.out, f.row_bytes / 4, off };
+        off += f.row_bytes / 4;
+        in_words += f.row_bytes / 4;
+        if (off > SLOT_MAX_ROW_WORDS)
+            return 0;
+        }
+    if (perm)
+        {
+        a.f[nf++] = SlotField { nullptr, perm, 1u, off };
+        off += 1;
+        }
+    if (off > SLOT_MAX_ROW_WORDS)
+        return 0;
+    a.nfields = nf;
+    a.row_words = off;
+    const char* eb = getenv("PGSD_B200_SLOT_BULK");
+    a.bulk = (aligned && !(eb && eb[0] == '0')) ? 1 : 0;
+    const char* ed = getenv("PGSD_B200_SLOT_DEBUG");
+    a.debug = ed ? atoi(ed) : 0;
+    SlotArgs a_place = a; // the interleaved copy is always 16-byte aligned
+    a_place.bulk = !(eb && eb[0] == '0') ? 1 : 0;
+
+    // slot bits: as few as keep the bucket count <= 32768
+    int L = SLOT_MIN_BITS;
+    const char* el = getenv("PGSD_B200_SLOT_BITS");
+    if (el)
+        L = atoi(el);
+    if (L < SLOT_MIN_BITS)
+        L = SLOT_MIN_BITS;
+    while (topbit - L > SLOT_MAX_BUCKET_BITS)
+        L++;
+    if (L > SLOT_MAX_BITS)
+        return 0;
+    const size_t place_smem = slot_place_smem(L, a.row_words);
+    if (place_smem > 220 * 1024)
+        return 0;
+    const int bbits = topbit > L ? topbit - L : 0;
+    const uint32_t nb = 1u << bbits;
+    const uint32_t bmask = nb - 1u;
+    const uint32_t cap = 1u << L;
+    if (n > (uint64_t)nb * cap)
+        return 0; // more keys than slots: duplicates for certain
+
+    int tile = 1024;
+    const char* et = getenv("PGSD_B200_SLOT_TILE");
+    if (et)
+        tile = atoi(et);
+    if (tile != 512 && tile != 1024 && tile != 2048)
+        tile = 1024;
+    while (tile > 512 && ((size_t)in_words + 1) * tile * 4 > 200 * 1024)
+        tile /= 2;
+    if (((size_t)in_words + 1) * tile * 4 > 200 * 1024)
+        return 0;
+
+    // The bucket cursors are spread out (one per 128-byte line by default): the L2 atomic unit serialises
+    // operations on the same sector, and 16384 packed cursors are only 2048 sectors.
+    uint32_t cstride = 32;
+    const char* ec = getenv("PGSD_B200_SLOT_CSTRIDE");
+    if (ec)
+        cstride = (uint32_t)atoi(ec);
+    if (cstride != 1 && cstride != 8 && cstride != 16 && cstride != 32 && cstride != 64)
+        cstride = 32;
+    // workspace: [flag 256 B][counts nb][base nb+1][cursors nb * cstride][interleaved copy + 256 B]
+    const char* ely = getenv("PGSD_B200_SLOT_LAYOUT");
+    const bool lines = ely && !strcmp(ely, "lines");
+    a.nbl = lines ? nb : 0u;
+    a_place.nbl = a.nbl;
+    const size_t tb = up256((size_t)(nb + 1) * 4);
+    const size_t cb = up256((size_t)nb * cstride * 4);
+    const size_t copy_bytes = lines ? (size_t)nb * (((size_t)cap * a.row_words * 4 + 127) / 128) * 128 : (size_t)n * a.row_words * 4;
+    const size_t need = 256 + 2 * tb + cb + up256(copy_bytes) + 256;
+    if (g_slot_ws_bytes < need)
+        {
+        if (g_slot_ws)
+            cudaFree(g_slot_ws);
+        g_slot_ws = nullptr;
+        g_slot_ws_bytes = 0;
+        if (cudaMalloc(&g_slot_ws, need) != cudaSuccess)
+            {
+            cudaGetLastError();
+            return 0; // the general path reports its own allocation failures
+            }
+        g_slot_ws_bytes = need;
+        }
+    if (!g_slot_flag_host && cudaHostAlloc((void**)&g_slot_flag_host, 256, cudaHostAllocDefault) != cudaSuccess)
+        {
+        cudaGetLastError();
+        return 0;
+        }
+    unsigned char* p = (unsigned char*)g_slot_ws;
+    uint32_t* flag = (uint32_t*)p;
+    uint32_t* counts = (uint32_t*)(p + 256);
+    uint32_t* base = (uint32_t*)(p + 256 + tb);
+    uint32_t* cursor = (uint32_t*)(p + 256 + 2 * tb);
+    uint32_t* aos = (uint32_t*)(p + 256 + 2 * tb + cb);
+
+    static bool attr_done = false;
+    if (!attr_done)
+        {
+        cudaFuncSetAttribute(k6_slot_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << SLOT_MAX_BUCKET_BITS) * 4);
+        cudaFuncSetAttribute(k6_slot_place, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        attr_done = true;
+        }
+    cudaMemsetAsync(p, 0, 256 + tb, st); // flag + counts
+    int hgrid = dev_sm_count() * (nb <= 16384 ? 2 : 1);
+    const uint64_t want = (n / 4 + 1023) / 1024;
+    if ((uint64_t)hgrid > want)
+        hgrid = want ? (int)want : 1;
+    k6_slot_hist<<<hgrid, 1024, (size_t)nb * 4, st>>>(keys, n, L, bmask, nb, counts);
+    k6_slot_scan<<<1, 1024, 0, st>>>(counts, nb, cap, (uint32_t)n, base, cursor, cstride, lines ? 1 : 0, flag);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess)
+        {
+        if (tile == 512)
+            e = launch_scatter<512, 128>(n, L, bmask, cursor, cstride, aos, flag, a, in_words, st);
+        else if (tile == 2048)
+            e = launch_scatter<2048, 512>(n, L, bmask, cursor, cstride, aos, flag, a, in_words, st);
+        else
+            e = launch_scatter<1024, 256>(n, L, bmask, cursor, cstride, aos, flag, a, in_words, st);
+        }
+    if (mark)
+        mark(0, st);
+    if (e == cudaSuccess)
+        {
+        k6_slot_place<<<nb, cap / 4, place_smem, st>>>(base, L, aos, flag, a_place);
+        e = cudaGetLastError();
+        }
+    if (mark)
+        mark(1, st);
+    dev_stats().kernel_launches += 4;
+    if (e != cudaSuccess)
+        {
+        set_last_error(std::string("reorder slot path launch: ") + cudaGetErrorString(e));
+        return -1;
+        }
+    cudaMemcpyAsync(g_slot_flag_host, flag, 8, cudaMemcpyDeviceToHost, st);
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess)
+        {
+        set_last_error(std::string("reorder slot path: ") + cudaGetErrorString(e));
+        return -1;
+        }
+    if (g_slot_flag_host[1] == 3)
+        {
+        set_last_error("reorder slot path: a bulk copy did not complete");
+        return -1;
+        }
+    *done = (g_slot_flag_host[0] == 0 && g_slot_flag_host[1] == 0) ? 1 : 0;
+    if (a.debug)
+        *done = 1; // timing experiments: the (wrong) result is kept
+    return 0;
+    }
+} // namespace pgsdb

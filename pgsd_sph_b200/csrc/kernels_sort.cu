@@ -1267,6 +1267,7 @@ void sort_release_workspace()
     if (g_census_host)
         cudaFreeHost(g_census_host);
     g_census_host = nullptr;
+    slot_release_workspace();
     }
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -1301,6 +1302,18 @@ int dev_reorder_phase_ms(float* out)
     for (int i = 0; i + 1 < g_phase_n; i++)
         cudaEventElapsedTime(&out[i], g_phase_ev[i], g_phase_ev[i + 1]);
     return 0;
+    }
+
+// phase marks of the slot path (kernels_slot.cu): scatter = "bucket pass", no pair passes, placement = "gather"
+static void slot_mark(int i, cudaStream_t st)
+    {
+    if (i == 0)
+        {
+        phase_mark(2, st);
+        phase_mark(3, st);
+        }
+    else
+        phase_mark(4, st);
     }
 
 static int rank_mode()
@@ -1679,6 +1692,15 @@ int dev_reorder_rows(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, ui
         for (int i = 0; i < nfields; i++)
             cudaMemcpyAsync(fields[i].out, fields[i].in, n * (size_t)fields[i].row_bytes, cudaMemcpyDeviceToDevice, st);
         return cudaGetLastError() == cudaSuccess ? 0 : -1;
+        }
+    // unique ids (the normal case): two passes over the rows, no ranking (kernels_slot.cu); duplicates are
+    // detected on the device and fall through to the stable general path below
+        {
+        int done = 0;
+        if ((rc = dev_reorder_slot(n, keys, keys_sorted, perm, nfields, fields, plan.topbit, stream_v, &done, slot_mark)) != 0)
+            return rc;
+        if (done)
+            return 0;
         }
     const bool direct = plan.npass == 1; // one varying byte: the bucket pass is the whole sort
     uint32_t row_words = perm ? 1u : 0u;

@@ -274,6 +274,7 @@ def bucket_key_cases():
 @pytest.mark.parametrize("name,keys", list(bucket_key_cases()), ids=[k for k, _ in bucket_key_cases()])
 def test_reorder_bucket_path_equals_stable_argsort(cuda, monkeypatch, name, keys, rank_mode):
     monkeypatch.setenv("PGSD_B200_BUCKET_MIN_ROWS", "0")
+    monkeypatch.setenv("PGSD_B200_SLOT", "0")   # the general (stable) path; the slot path has its own tests below
     monkeypatch.setenv("PGSD_B200_RANK_MODE", rank_mode)
     n = len(keys)
     rng = np.random.default_rng(n)
@@ -292,6 +293,7 @@ def test_reorder_bucket_path_equals_stable_argsort(cuda, monkeypatch, name, keys
 def test_reorder_bucket_path_wide_rows(cuda, monkeypatch):
     """Rows wider than the staging buffer share (16 words) take several staging rounds."""
     monkeypatch.setenv("PGSD_B200_BUCKET_MIN_ROWS", "0")
+    monkeypatch.setenv("PGSD_B200_SLOT", "0")
     rng = np.random.default_rng(3)
     n = 30011
     keys = rng.permutation(n).astype(np.uint32)
@@ -319,6 +321,7 @@ def test_reorder_bucket_layouts_and_row_widths(cuda, monkeypatch, widths, layout
     """Interleaved (AoS) bucketed copy at 4/2/1 items per thread, its 40-word limit (wider rows take
     the per-field copy), and the per-field layout forced by environment."""
     monkeypatch.setenv("PGSD_B200_BUCKET_MIN_ROWS", "0")
+    monkeypatch.setenv("PGSD_B200_SLOT", "0")
     monkeypatch.setenv("PGSD_B200_BUCKET_LAYOUT", layout)
     rng = np.random.default_rng(sum(widths))
     n = 50021
@@ -332,6 +335,138 @@ def test_reorder_bucket_layouts_and_row_widths(cuda, monkeypatch, widths, layout
             assert (p == o.astype(np.uint32)).all()
         for f, g in zip(fields, outs):
             assert g.tobytes() == f[o].tobytes()
+
+
+# ---- slot path (kernels_slot.cu): unique ids -> fine bucket scatter + per-bucket slot placement
+def _launches(lib):
+    st = _lib.Stats()
+    lib.pgsd_b200_get_stats(st)
+    return int(st.kernel_launches)
+
+
+SLOT_LAUNCHES = 5   # census + histogram + scan + scatter + place; anything more = the general path ran
+
+
+def slot_key_cases():
+    rng = np.random.default_rng(41)
+    yield "perm_1", np.array([0], dtype=np.uint32), None                             # nothing varies: identity
+    yield "perm_1000", rng.permutation(1000).astype(np.uint32), True
+    yield "perm_1024", rng.permutation(1024).astype(np.uint32), True                 # exactly one full bucket
+    yield "perm_1025", rng.permutation(1025).astype(np.uint32), True
+    yield "perm_70k", rng.permutation(70001).astype(np.uint32), True
+    yield "perm_300k", rng.permutation(300000).astype(np.uint32), True
+    yield "perm_1Mi", rng.permutation(1 << 20).astype(np.uint32), True
+    yield "sorted", np.arange(123457, dtype=np.uint32), True                         # every row of a tile hits one cursor
+    yield "reversed", np.arange(99999, dtype=np.uint32)[::-1].copy(), True
+    yield "even_ids", (rng.permutation(200003) * 2).astype(np.uint32), True          # half-empty buckets: compaction
+    yield "sparse_unique", rng.choice(1 << 22, size=150001, replace=False).astype(np.uint32), True
+    yield "const_high_bits", (rng.permutation(50000) + 0xABC00000).astype(np.uint32), True
+    yield "gaps_and_offset", (rng.permutation(40000) * 3 + 77777).astype(np.uint32), True
+    yield "one_dup_pair", np.concatenate([rng.permutation(90000), [4242]]).astype(np.uint32), False
+    yield "dups_2bytes", rng.integers(0, 40000, size=123457).astype(np.uint32), False  # bucket overflow -> flag in the scan
+    yield "dups_low_density", rng.integers(0, 1 << 22, size=100000).astype(np.uint32), False  # dups found by the placement
+    yield "full_32bit", rng.choice(1 << 32, size=100003, replace=False).astype(np.uint32), None  # too many buckets: not applicable
+
+
+@pytest.mark.parametrize("layout", ["flat", "lines"])
+@pytest.mark.parametrize("name,keys,slot", list(slot_key_cases()), ids=[k for k, _, _ in slot_key_cases()])
+def test_reorder_slot_path_equals_stable_argsort(cuda, monkeypatch, name, keys, slot, layout):
+    """Unique ids take the slot path (counted by its kernel launches); duplicate ids are detected on the
+    device and the stable general path produces the result.  Either way: == stable argsort + gather."""
+    monkeypatch.setenv("PGSD_B200_BUCKET_MIN_ROWS", "0")
+    monkeypatch.setenv("PGSD_B200_SLOT_LAYOUT", layout)
+    n = len(keys)
+    rng = np.random.default_rng(n)
+    fields = [rng.standard_normal((n, 3)).astype(np.float32), rng.standard_normal((n, 3)).astype(np.float32),
+              rng.standard_normal(n).astype(np.float32), rng.standard_normal(n).astype(np.float32),
+              rng.integers(0, 3, size=n).astype(np.uint32)]
+    o = np.argsort(keys, kind='stable')
+    for want_perm in (True, False):
+        cuda.pgsd_b200_reset_stats()
+        s, p, outs = _reorder_device_full(cuda, keys, fields, want_perm)
+        launches = _launches(cuda)
+        assert (s == keys[o]).all()
+        if want_perm:
+            assert (p == o.astype(np.uint32)).all()
+        for f, g in zip(fields, outs):
+            assert g.tobytes() == f[o].tobytes()
+        if slot is True:
+            assert launches == SLOT_LAUNCHES, launches
+        elif slot is False:
+            assert launches > SLOT_LAUNCHES, launches
+
+
+@pytest.mark.parametrize("bulk", ["1", "0", "lines"])
+@pytest.mark.parametrize("tile", ["512", "1024", "2048"])
+@pytest.mark.parametrize("bits", ["10", "11", "12"])
+def test_reorder_slot_path_variants(cuda, monkeypatch, bits, tile, bulk):
+    """Slot bits (bucket capacity 1024/2048/4096), scatter tile sizes, and the plain-load staging."""
+    monkeypatch.setenv("PGSD_B200_BUCKET_MIN_ROWS", "0")
+    monkeypatch.setenv("PGSD_B200_SLOT_BITS", bits)
+    monkeypatch.setenv("PGSD_B200_SLOT_TILE", tile)
+    if bulk == "lines":
+        monkeypatch.setenv("PGSD_B200_SLOT_LAYOUT", "lines")
+    else:
+        monkeypatch.setenv("PGSD_B200_SLOT_BULK", bulk)
+    rng = np.random.default_rng(int(bits) * 7 + int(tile))
+    n = 150001
+    keys = (rng.permutation(n) + rng.integers(0, 2)).astype(np.uint32)
+    fields = [rng.integers(0, 2 ** 32, size=(n, 3), dtype=np.uint64).astype(np.uint32), rng.standard_normal(n),
+              rng.integers(0, 2 ** 32, size=n, dtype=np.uint64).astype(np.uint32)]
+    o = np.argsort(keys, kind='stable')
+    cuda.pgsd_b200_reset_stats()
+    s, p, outs = _reorder_device_full(cuda, keys, fields, True)
+    assert _launches(cuda) == SLOT_LAUNCHES
+    assert (s == keys[o]).all() and (p == o.astype(np.uint32)).all()
+    for f, g in zip(fields, outs):
+        assert g.tobytes() == f[o].tobytes()
+
+
+@pytest.mark.parametrize("layout", ["flat", "lines"])
+@pytest.mark.parametrize("widths", [(1,), (2, 2), (3, 3, 1, 1, 1), (4, 4, 4, 4), (5, 7), (16, 14), (16, 16)])
+def test_reorder_slot_path_row_widths(cuda, monkeypatch, widths, layout):
+    """Records of 2..31 words take the slot path; wider records fall back to the general path."""
+    monkeypatch.setenv("PGSD_B200_BUCKET_MIN_ROWS", "0")
+    monkeypatch.setenv("PGSD_B200_SLOT_LAYOUT", layout)
+    rng = np.random.default_rng(sum(widths))
+    n = 70001
+    keys = rng.permutation(n).astype(np.uint32)
+    fields = [rng.integers(0, 2 ** 32, size=(n, w), dtype=np.uint64).astype(np.uint32) for w in widths]
+    o = np.argsort(keys, kind='stable')
+    for want_perm in (True, False):
+        cuda.pgsd_b200_reset_stats()
+        s, p, outs = _reorder_device_full(cuda, keys, fields, want_perm)
+        took_slot = _launches(cuda) == SLOT_LAUNCHES
+        assert took_slot == (1 + sum(widths) + (1 if want_perm else 0) <= 32)
+        assert (s == keys[o]).all()
+        if want_perm:
+            assert (p == o.astype(np.uint32)).all()
+        for f, g in zip(fields, outs):
+            assert g.tobytes() == f[o].tobytes()
+
+
+def test_reorder_slot_path_unaligned_inputs(cuda, monkeypatch):
+    """Field arrays that start 4 bytes off a 16-byte boundary are staged with plain loads."""
+    monkeypatch.setenv("PGSD_B200_BUCKET_MIN_ROWS", "0")
+    rng = np.random.default_rng(77)
+    n = 50000
+    keys = rng.permutation(n).astype(np.uint32)
+    pos = rng.standard_normal((n, 3)).astype(np.float32)
+    dens = rng.standard_normal(n).astype(np.float32)
+    dk = DeviceArray.from_numpy(keys)
+    dpos = DeviceArray.from_numpy(np.concatenate([np.zeros(1, np.float32), pos.ravel()]))
+    ddens = DeviceArray.from_numpy(np.concatenate([np.zeros(1, np.float32), dens]))
+    opos, odens = DeviceArray((n * 3 + 1,), np.float32), DeviceArray((n + 1,), np.float32)
+    ds = DeviceArray((n,), np.uint32)
+    fl_ = (_lib.Field * 2)(_lib.Field(dpos.ptr + 4, opos.ptr + 4, 12), _lib.Field(ddens.ptr + 4, odens.ptr + 4, 4))
+    cuda.pgsd_b200_reset_stats()
+    _lib.check(cuda.pgsd_b200_reorder_device(n, dk.ptr, ds.ptr, None, 2, fl_, None), "reorder_device")
+    _lib.check(cuda.pgsd_b200_synchronize(), "sync")
+    assert _launches(cuda) == SLOT_LAUNCHES
+    o = np.argsort(keys, kind='stable')
+    assert (ds.to_numpy() == keys[o]).all()
+    assert opos.to_numpy()[1:].tobytes() == pos[o].tobytes()
+    assert odens.to_numpy()[1:].tobytes() == dens[o].tobytes()
 
 
 @pytest.mark.parametrize("M", [1, 2, 3, 4])
