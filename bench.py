@@ -255,8 +255,9 @@ def run_read_leg(lib, dist, args, peaks, windows):
     fields = (_lib.Field * 5)(*[_lib.Field(i.ptr, o.ptr, a.dtype.itemsize * (a.shape[1] if a.ndim > 1 else 1))
                                 for i, o, a in zip(d_in, d_out, host_fields)])
 
-    def step_dev():
-        _lib.check(lib.pgsd_b200_reorder_device(n, d_ids.ptr, d_sorted.ptr, d_perm.ptr, 5, fields, None), "reorder")
+    def step_dev(perm=None):
+        # the call pgsd.hoomd makes (hoomd.py reorder_by_id): ids + 5 fields, no permutation output
+        _lib.check(lib.pgsd_b200_reorder_device(n, d_ids.ptr, d_sorted.ptr, perm, 5, fields, None), "reorder")
 
     for _ in range(args.warmup):
         step_dev()
@@ -290,6 +291,11 @@ def run_read_leg(lib, dist, args, peaks, windows):
     # parity spot check of the timed configuration: sortedness + id->row consistency (size independent)
     got_ids = d_sorted.to_numpy()
     assert np.array_equal(got_ids, np.arange(n, dtype=np.uint32)), "reordered ids are not 0..N-1"
+    got_pos = d_out[0].to_numpy()
+    step_dev(d_perm.ptr)   # untimed: same reorder, this time also returning the permutation for the checks below
+    lib.pgsd_b200_synchronize()
+    assert np.array_equal(d_sorted.to_numpy(), got_ids) and np.array_equal(d_out[0].to_numpy(), got_pos)
+    del got_pos
     perm = d_perm.to_numpy()
     assert np.array_equal(cols[9][perm], got_ids), "perm does not sort the ids"
     chk = np.random.default_rng(1).integers(0, n, size=4096)
@@ -337,12 +343,21 @@ def run_read_leg(lib, dist, args, peaks, windows):
         return {"ms": ms, "algorithmic_bytes": bytes_pp * n, "GBps": bytes_pp * n / t / 1e9,
                 "frac": bytes_pp * n / t / 1e9 / peak, "note": note}
 
-    kernels = {
-        "k4_digit_census": kern(phase_ms[0], 4, "keys read once; includes the 8 KB D2H + host sync"),
-        "k4_bucket_rows": kern(phase_ms[1], 4 + 2 * 40, "tile histogram (4 B) + rows moved once: 40 B read + 40 B written"),
-        "k4_pair_passes": kern(phase_ms[2], 2 * 4 + (4 + 8) + 16, "2 segmented LSD passes inside buckets: histogram 4 B each; (key,idx) 12 + 16 B"),
-        "k5_gather": kern(phase_ms[3], 4 + 2 * 36, "perm 4 B + 36 B payload read + 36 B written"),
-    }
+    slot = os.environ.get("PGSD_B200_SLOT", "1") != "0" and phase_ms[2] < 0.02   # unique ids: no pair passes ran
+    if slot:
+        kernels = {
+            "k4_digit_census": kern(phase_ms[0], 4, "keys read once; includes the 8 KB D2H + host sync"),
+            "k6_slot_hist+scan+scatter": kern(phase_ms[1], 4 + 2 * 40, "bucket histogram (4 B) + rows moved once into "
+                                              "interleaved records: 40 B read + 40 B written (one cursor atomic per row)"),
+            "k6_slot_place": kern(phase_ms[3], 2 * 40, "one CTA per bucket: 40 B records read, 40 B of fields written"),
+        }
+    else:
+        kernels = {
+            "k4_digit_census": kern(phase_ms[0], 4, "keys read once; includes the 8 KB D2H + host sync"),
+            "k4_bucket_rows": kern(phase_ms[1], 4 + 2 * 40, "tile histogram (4 B) + rows moved once: 40 B read + 40 B written"),
+            "k4_pair_passes": kern(phase_ms[2], 2 * 4 + (4 + 8) + 16, "2 segmented LSD passes inside buckets: histogram 4 B each; (key,idx) 12 + 16 B"),
+            "k5_gather": kern(phase_ms[3], 4 + 2 * 36, "perm 4 B + 36 B payload read + 36 B written"),
+        }
     reorder_s = dev_ms * 1e-3 / args.steps
     return {
         "metric": "id_reordered_read_Mparticles_per_s", "value": value, "unit": "Mparticles/s",
@@ -355,7 +370,8 @@ def run_read_leg(lib, dist, args, peaks, windows):
         "roofline": {"bound": "hbm", "achieved": 80 * n / reorder_s / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": 80 * n / reorder_s / 1e9 / peak, "traffic": None, "peak_source": peaks["source"],
                      "what": "K4+K5 reorder as one operation: 80 B/particle algorithmic"},
-        "kernels": kernels, "gpu_launches": int(launches),
+        "kernels": kernels, "reorder_path": "slot (unique ids)" if slot else "general (stable LSD)",
+        "gpu_launches": int(launches),
     }
 
 

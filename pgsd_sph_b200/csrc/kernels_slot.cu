@@ -7,20 +7,36 @@
 //
 //   k6_slot_hist     histogram of the key bits above the low L ("slot") bits: <= 32768 buckets of at most
 //                    CAP = 2^L keys each.  A bucket with more than CAP keys proves a duplicate -> flag.
-//   k6_slot_scan     exclusive scan of the bucket counts (one CTA) -> bucket bases and write cursors.
+//   k6_slot_scan     exclusive scan of the bucket counts (one CTA) -> bucket bases (output rows).
 //   k6_slot_scatter  rows (key + all fields [+ original index]) are staged SoA -> shared memory with one
-//                    TMA bulk copy per field, every row takes the next free position of its bucket
-//                    (one global atomic per row), and leaves as one interleaved record.  Buckets are
-//                    contiguous in the interleaved copy, in key order.
-//   k6_slot_place    one CTA per bucket: the bucket (<= CAP rows, 40 KB for the SPH schema) comes in with
-//                    ONE TMA bulk copy, every row is placed at slot = key & (CAP-1) (an occupancy bitmap
+//                    TMA bulk copy per field (the keys go straight to registers, so the atomics below are
+//                    in flight while the payload arrives), every row takes the next free position of its
+//                    bucket (one global atomic per row on a cursor that has a 128-byte line of its own),
+//                    and leaves as one interleaved record (a group of lanes per record, 64-bit stores).
+//   k6_slot_place    one CTA per bucket: the bucket (<= CAP records, 40 KB for the SPH schema) comes into
+//                    shared memory, every record is placed at slot = key & (CAP-1) (an occupancy bitmap
 //                    detects duplicates and compacts gaps), and the fields are written back SoA, fully
 //                    coalesced, at the bucket's own output range.
+//
+// Layout of the interleaved copy ("lines", default): 128-byte line j of bucket b is line j * nb + b.  The
+// cursors of all buckets advance at about the same pace, so the lines being filled form ONE compact window
+// that moves through the copy, and the L2 write-backs of completed lines fall into few open DRAM rows.
+// With contiguous buckets ("flat", PGSD_B200_SLOT_LAYOUT=flat: one TMA bulk copy per bucket in
+// k6_slot_place) the nb write frontiers are spread over the whole copy: scatter 0.61 ms instead of 0.50 ms
+// at 16 Mi particles.
 //
 // Bytes moved: 4 (hist) + 40 + 40 (scatter) + 40 + 40 (place) = 164 B/particle for the 40-byte SPH row,
 // against 200 B/particle of the general path (bucket pass + 2 segmented pair passes + gather), and none
 // of its ballot ranking.  When a duplicate key is found (flag), nothing of the result is trusted: the
 // caller falls back to the stable general path of kernels_sort.cu.
+//
+// Measured on B200, 16 Mi particles (profiles/README.md, r2): place 0.215 ms = 0.95 of the measured HBM
+// copy rate; scatter 0.50 ms, which decomposes (PGSD_B200_SLOT_DEBUG timing experiments, flat layout) into
+// staging 0.12 + cursor atomics 0.16-0.20 + record stores 0.11 (+ 0.17 when they go to their scattered
+// places) -- additive although no unit is above 35 % busy in ncu: DRAM spends its time opening rows for the
+// write-backs, not transferring.  Tried without gain: a persistent double-buffered variant that overlaps
+// TMA, atomics and stores inside the CTA (0.55 ms), L2 evict-first loads (0.57 ms), packed / 32-byte /
+// 256-byte cursor strides (+-3 %), tiles of 512 / 2048 rows (+-5 %).
 //
 // sm_100a only (cp.async.bulk + mbarrier).  No CPU fallback.
 #include "device_internal.h"
@@ -205,6 +221,95 @@ __global__ void __launch_bounds__(1024) k6_slot_scan(const uint32_t* __restrict_
         flag[0] = 1;
     }
 
+// records out: a group of lanes writes one record (consecutive words), G records per warp store
+template <int NT>
+__device__ __forceinline__ void slot_records_out(const uint32_t* __restrict__ raw, const uint32_t* __restrict__ sdst,
+                                                 const uint32_t* __restrict__ col, uint64_t tile0, uint32_t tile_n,
+                                                 uint32_t RW, uint32_t* __restrict__ aos, const SlotArgs& args, int lane, int w)
+    {
+    constexpr uint32_t NW = NT / 32;
+    constexpr int U = 4;
+    if ((RW & 1u) == 0)
+        {
+        const uint32_t R2 = RW / 2, G = 32u / R2;
+        const uint32_t g = (uint32_t)lane / R2, c2 = (uint32_t)lane - g * R2;
+        if (g < G)
+            {
+            const uint32_t ca = col[2 * c2], cb = col[2 * c2 + 1];
+            const uint32_t Wa = ca & 255u, fa = ca >> 8, Wb = cb & 255u, fb = cb >> 8;
+            uint2* aos2 = reinterpret_cast<uint2*>(aos);
+            const uint32_t step = NW * G;
+            for (uint32_t r0 = (uint32_t)w * G + g; r0 < tile_n; r0 += step * U)
+                {
+                uint32_t dd[U];
+                uint2 v[U];
+#pragma unroll
+                for (int u = 0; u < U; u++)
+                    {
+                    const uint32_t r = r0 + (uint32_t)u * step;
+                    if (r < tile_n)
+                        {
+                        dd[u] = sdst[r];
+                        v[u].x = Wa ? raw[fa + r * Wa] : (uint32_t)(tile0 + r);
+                        v[u].y = Wb ? raw[fb + r * Wb] : (uint32_t)(tile0 + r);
+                        }
+                    }
+#pragma unroll
+                for (int u = 0; u < U; u++)
+                    if (r0 + (uint32_t)u * step < tile_n)
+                        {
+                        if (args.nbl)
+                            {
+                            const uint32_t o = (dd[u] & 4095u) * (RW * 4u) + c2 * 8u;
+                            const uint64_t at = ((uint64_t)((o >> 7) * args.nbl + (dd[u] >> 12)) << 7) + (o & 127u);
+                            *reinterpret_cast<uint2*>(reinterpret_cast<unsigned char*>(aos) + at) = v[u];
+                            }
+                        else
+                            aos2[(uint64_t)dd[u] * R2 + c2] = v[u];
+                        }
+                }
+            }
+        }
+    else
+        {
+        const uint32_t G = 32u / RW;
+        const uint32_t g = (uint32_t)lane / RW, c = (uint32_t)lane - g * RW;
+        if (g < G)
+            {
+            const uint32_t cc = col[c];
+            const uint32_t W = cc & 255u, fb = cc >> 8;
+            const uint32_t step = NW * G;
+            for (uint32_t r0 = (uint32_t)w * G + g; r0 < tile_n; r0 += step * U)
+                {
+                uint32_t dd[U], v[U];
+#pragma unroll
+                for (int u = 0; u < U; u++)
+                    {
+                    const uint32_t r = r0 + (uint32_t)u * step;
+                    if (r < tile_n)
+                        {
+                        dd[u] = sdst[r];
+                        v[u] = W ? raw[fb + r * W] : (uint32_t)(tile0 + r);
+                        }
+                    }
+#pragma unroll
+                for (int u = 0; u < U; u++)
+                    if (r0 + (uint32_t)u * step < tile_n)
+                        {
+                        if (args.nbl)
+                            {
+                            const uint32_t o = (dd[u] & 4095u) * (RW * 4u) + c * 4u;
+                            const uint64_t at = ((uint64_t)((o >> 7) * args.nbl + (dd[u] >> 12)) << 7) + (o & 127u);
+                            *reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(aos) + at) = v[u];
+                            }
+                        else
+                            aos[(uint64_t)dd[u] * RW + c] = v[u];
+                        }
+                }
+            }
+        }
+    }
+
 // ---- scatter: every row to the next free position of its bucket, as one interleaved record -------------
 // Field tiles sit field-major in shared memory, tile i shifted by 4 * i words so that the columns of one
 // record fall into different banks.  The keys (field 0) are loaded straight into registers: their atomics
@@ -212,7 +317,7 @@ __global__ void __launch_bounds__(1024) k6_slot_scan(const uint32_t* __restrict_
 constexpr uint32_t SLOT_SKEW = 4; // words; keeps every tile 16-byte aligned for the bulk copies
 
 template <int T, int NT>
-__global__ void __launch_bounds__(NT) k6_slot_scatter(uint64_t n, int L, uint32_t bmask, uint32_t* __restrict__ cursor,
+__global__ void __launch_bounds__(NT) k6_slot_scatter(uint64_t n, uint32_t tile_first, int L, uint32_t bmask, uint32_t* __restrict__ cursor,
                                                      uint32_t cstride, uint32_t* __restrict__ aos, uint32_t* __restrict__ flag,
                                                      const __grid_constant__ SlotArgs args)
     {
@@ -223,7 +328,7 @@ __global__ void __launch_bounds__(NT) k6_slot_scatter(uint64_t n, int L, uint32_
     if (flag[0] != 0) // written by k6_slot_scan only: uniform
         return;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const uint64_t tile0 = (uint64_t)blockIdx.x * T;
+    const uint64_t tile0 = ((uint64_t)blockIdx.x + tile_first) * T;
     const uint32_t tile_n = (uint32_t)((n - tile0) < (uint64_t)T ? (n - tile0) : T);
     const uint32_t RW = args.row_words;
     constexpr int PER = T / NT;
@@ -339,88 +444,8 @@ __global__ void __launch_bounds__(NT) k6_slot_scatter(uint64_t n, int L, uint32_
             aos[tid] = raw[tid];
         return;
         }
-    // (3) records out: a group of lanes writes one record (consecutive words), G records per warp store
-    constexpr uint32_t NW = NT / 32;
-    constexpr int U = 4;
-    if ((RW & 1u) == 0)
-        {
-        const uint32_t R2 = RW / 2, G = 32u / R2;
-        const uint32_t g = (uint32_t)lane / R2, c2 = (uint32_t)lane - g * R2;
-        if (g < G)
-            {
-            const uint32_t ca = col[2 * c2], cb = col[2 * c2 + 1];
-            const uint32_t Wa = ca & 255u, fa = ca >> 8, Wb = cb & 255u, fb = cb >> 8;
-            uint2* aos2 = reinterpret_cast<uint2*>(aos);
-            const uint32_t step = NW * G;
-            for (uint32_t r0 = (uint32_t)w * G + g; r0 < tile_n; r0 += step * U)
-                {
-                uint32_t dd[U];
-                uint2 v[U];
-#pragma unroll
-                for (int u = 0; u < U; u++)
-                    {
-                    const uint32_t r = r0 + (uint32_t)u * step;
-                    if (r < tile_n)
-                        {
-                        dd[u] = sdst[r];
-                        v[u].x = Wa ? raw[fa + r * Wa] : (uint32_t)(tile0 + r);
-                        v[u].y = Wb ? raw[fb + r * Wb] : (uint32_t)(tile0 + r);
-                        }
-                    }
-#pragma unroll
-                for (int u = 0; u < U; u++)
-                    if (r0 + (uint32_t)u * step < tile_n)
-                        {
-                        if (args.nbl)
-                            {
-                            const uint32_t o = (dd[u] & 4095u) * (RW * 4u) + c2 * 8u;
-                            const uint64_t at = ((uint64_t)((o >> 7) * args.nbl + (dd[u] >> 12)) << 7) + (o & 127u);
-                            *reinterpret_cast<uint2*>(reinterpret_cast<unsigned char*>(aos) + at) = v[u];
-                            }
-                        else
-                            aos2[(uint64_t)dd[u] * R2 + c2] = v[u];
-                        }
-                }
-            }
-        }
-    else
-        {
-        const uint32_t G = 32u / RW;
-        const uint32_t g = (uint32_t)lane / RW, c = (uint32_t)lane - g * RW;
-        if (g < G)
-            {
-            const uint32_t cc = col[c];
-            const uint32_t W = cc & 255u, fb = cc >> 8;
-            const uint32_t step = NW * G;
-            for (uint32_t r0 = (uint32_t)w * G + g; r0 < tile_n; r0 += step * U)
-                {
-                uint32_t dd[U], v[U];
-#pragma unroll
-                for (int u = 0; u < U; u++)
-                    {
-                    const uint32_t r = r0 + (uint32_t)u * step;
-                    if (r < tile_n)
-                        {
-                        dd[u] = sdst[r];
-                        v[u] = W ? raw[fb + r * W] : (uint32_t)(tile0 + r);
-                        }
-                    }
-#pragma unroll
-                for (int u = 0; u < U; u++)
-                    if (r0 + (uint32_t)u * step < tile_n)
-                        {
-                        if (args.nbl)
-                            {
-                            const uint32_t o = (dd[u] & 4095u) * (RW * 4u) + c * 4u;
-                            const uint64_t at = ((uint64_t)((o >> 7) * args.nbl + (dd[u] >> 12)) << 7) + (o & 127u);
-                            *reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(aos) + at) = v[u];
-                            }
-                        else
-                            aos[(uint64_t)dd[u] * RW + c] = v[u];
-                        }
-                }
-            }
-        }
+    // (3) records out
+    slot_records_out<NT>(raw, sdst, col, tile0, tile_n, RW, aos, args, lane, w);
     }
 
 // ---- place: one CTA per bucket; slot = key & (CAP-1) is the row's rank among the bucket's (unique) keys ---
@@ -612,8 +637,9 @@ static size_t slot_place_smem(int L, uint32_t rw)
     }
 
 template <int T, int NT>
-static cudaError_t launch_scatter(uint64_t n, int L, uint32_t bmask, uint32_t* cursor, uint32_t cstride, uint32_t* aos, uint32_t* flag,
-                                  const SlotArgs& a, uint32_t in_words, cudaStream_t st)
+static cudaError_t launch_scatter(uint64_t n, uint32_t tile_first, uint32_t tiles, int L, uint32_t bmask, uint32_t* cursor,
+                                  uint32_t cstride, uint32_t* aos, uint32_t* flag, const SlotArgs& a, uint32_t in_words,
+                                  cudaStream_t st)
     {
     const size_t smem = ((size_t)in_words + 1) * T * 4 + SLOT_MAX_FIELDS * SLOT_SKEW * 4;
     static size_t attr = 0;
@@ -624,8 +650,10 @@ static cudaError_t launch_scatter(uint64_t n, int L, uint32_t bmask, uint32_t* c
             return e;
         attr = smem;
         }
-    const uint64_t tiles = (n + T - 1) / T;
-    k6_slot_scatter<T, NT><<<(unsigned)tiles, NT, smem, st>>>(n, L, bmask, cursor, cstride, aos, flag, a);
+    if (tiles == 0)
+        return cudaSuccess;
+    k6_slot_scatter<T, NT><<<tiles, NT, smem, st>>>(n, tile_first, L, bmask, cursor, cstride, aos, flag, a);
+    dev_stats().kernel_launches++;
     return cudaGetLastError();
     }
 
@@ -725,7 +753,7 @@ int dev_reorder_slot(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, ui
         cstride = 32;
     // workspace: [flag 256 B][counts nb][base nb+1][cursors nb * cstride][interleaved copy + 256 B]
     const char* ely = getenv("PGSD_B200_SLOT_LAYOUT");
-    const bool lines = ely && !strcmp(ely, "lines");
+    const bool lines = !(ely && !strcmp(ely, "flat"));
     a.nbl = lines ? nb : 0u;
     a_place.nbl = a.nbl;
     const size_t tb = up256((size_t)(nb + 1) * 4);
@@ -771,15 +799,17 @@ int dev_reorder_slot(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, ui
         hgrid = want ? (int)want : 1;
     k6_slot_hist<<<hgrid, 1024, (size_t)nb * 4, st>>>(keys, n, L, bmask, nb, counts);
     k6_slot_scan<<<1, 1024, 0, st>>>(counts, nb, cap, (uint32_t)n, base, cursor, cstride, lines ? 1 : 0, flag);
+    dev_stats().kernel_launches += 2;
     cudaError_t e = cudaGetLastError();
+    const uint32_t tiles_all = (uint32_t)((n + tile - 1) / tile);
     if (e == cudaSuccess)
         {
         if (tile == 512)
-            e = launch_scatter<512, 128>(n, L, bmask, cursor, cstride, aos, flag, a, in_words, st);
+            e = launch_scatter<512, 128>(n, 0, tiles_all, L, bmask, cursor, cstride, aos, flag, a, in_words, st);
         else if (tile == 2048)
-            e = launch_scatter<2048, 512>(n, L, bmask, cursor, cstride, aos, flag, a, in_words, st);
+            e = launch_scatter<2048, 512>(n, 0, tiles_all, L, bmask, cursor, cstride, aos, flag, a, in_words, st);
         else
-            e = launch_scatter<1024, 256>(n, L, bmask, cursor, cstride, aos, flag, a, in_words, st);
+            e = launch_scatter<1024, 256>(n, 0, tiles_all, L, bmask, cursor, cstride, aos, flag, a, in_words, st);
         }
     if (mark)
         mark(0, st);
@@ -790,7 +820,7 @@ int dev_reorder_slot(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, ui
         }
     if (mark)
         mark(1, st);
-    dev_stats().kernel_launches += 4;
+    dev_stats().kernel_launches++;
     if (e != cudaSuccess)
         {
         set_last_error(std::string("reorder slot path launch: ") + cudaGetErrorString(e));

@@ -1623,6 +1623,12 @@ static uint64_t bucket_min_rows()
     return e ? (uint64_t)atoll(e) : (1ull << 20);
     }
 
+static uint64_t slot_min_rows()
+    {
+    const char* e = getenv("PGSD_B200_SLOT_MIN_ROWS");
+    return e ? (uint64_t)atoll(e) : 2048ull;
+    }
+
 int dev_reorder_rows(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, uint32_t* perm, int nfields,
                      const ReorderField* fields, void* stream_v)
     {
@@ -1652,6 +1658,27 @@ int dev_reorder_rows(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, ui
         }
     if (!rows_ok || n < bucket_min_rows())
         {
+        // small frames with unique ids: the slot path (kernels_slot.cu) is 5 launches instead of ~10
+        if (rows_ok && n >= slot_min_rows())
+            {
+            if ((rc = sort_setup()) != 0)
+                return rc;
+            void* ws = nullptr;
+            if ((rc = ws_reserve(g_sort_ws, 4 * align_up((size_t)n * 4, 256) + pass_tables_bytes(n), &ws)) != 0)
+                return rc;
+            const PassTables t = pass_tables_at((unsigned char*)ws + 4 * align_up((size_t)n * 4, 256), n);
+            KeyPlan plan;
+            if ((rc = key_census(n, keys, t, st, &plan)) != 0)
+                return rc;
+            if (plan.npass > 0)
+                {
+                int done = 0;
+                if ((rc = dev_reorder_slot(n, keys, keys_sorted, perm, nfields, fields, plan.topbit, stream_v, &done, nullptr)) != 0)
+                    return rc;
+                if (done)
+                    return 0;
+                }
+            }
         // small or oddly shaped frames: pair sort + gather from the caller's arrays
         uint32_t* p = perm;
         if (p == nullptr)

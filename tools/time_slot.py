@@ -18,24 +18,14 @@ VARIANTS = [
     ("slot tile 2048", {"PGSD_B200_SLOT_TILE": "2048"}),
     ("slot bits 11", {"PGSD_B200_SLOT_BITS": "11"}),
     ("slot bits 12", {"PGSD_B200_SLOT_BITS": "12"}),
-    ("slot plain loads", {"PGSD_B200_SLOT_BULK": "0"}),
-    ("slot lines", {"PGSD_B200_SLOT_LAYOUT": "lines"}),
-    ("slot lines tile 512", {"PGSD_B200_SLOT_LAYOUT": "lines", "PGSD_B200_SLOT_TILE": "512"}),
-    ("slot lines tile 2048", {"PGSD_B200_SLOT_LAYOUT": "lines", "PGSD_B200_SLOT_TILE": "2048"}),
-    ("slot lines bits 11", {"PGSD_B200_SLOT_LAYOUT": "lines", "PGSD_B200_SLOT_BITS": "11"}),
-    ("slot cstride 1", {"PGSD_B200_SLOT_CSTRIDE": "1"}),
-    ("slot cstride 8", {"PGSD_B200_SLOT_CSTRIDE": "8"}),
-    ("slot cstride 64", {"PGSD_B200_SLOT_CSTRIDE": "64"}),
-    ("slot cstride 8 tile 512", {"PGSD_B200_SLOT_CSTRIDE": "8", "PGSD_B200_SLOT_TILE": "512"}),
-    ("dbg1 no atomics, identity", {"PGSD_B200_SLOT_DEBUG": "1"}),
-    ("dbg2 atomics, identity", {"PGSD_B200_SLOT_DEBUG": "2"}),
-    ("dbg3 atomics, no records", {"PGSD_B200_SLOT_DEBUG": "3"}),
-    ("dbg4 staging only", {"PGSD_B200_SLOT_DEBUG": "4"}),
-    ("dbg1 tile 512", {"PGSD_B200_SLOT_DEBUG": "1", "PGSD_B200_SLOT_TILE": "512"}),
-    ("dbg2 tile 512", {"PGSD_B200_SLOT_DEBUG": "2", "PGSD_B200_SLOT_TILE": "512"}),
-    ("dbg3 tile 512", {"PGSD_B200_SLOT_DEBUG": "3", "PGSD_B200_SLOT_TILE": "512"}),
-    ("dbg4 tile 512", {"PGSD_B200_SLOT_DEBUG": "4", "PGSD_B200_SLOT_TILE": "512"}),
-    ("dbg4 plain loads", {"PGSD_B200_SLOT_DEBUG": "4", "PGSD_B200_SLOT_BULK": "0"}),
+    ("slot flat", {"PGSD_B200_SLOT_LAYOUT": "flat"}),
+    ("slot flat plain loads", {"PGSD_B200_SLOT_LAYOUT": "flat", "PGSD_B200_SLOT_BULK": "0"}),
+    ("slot flat cstride 1", {"PGSD_B200_SLOT_LAYOUT": "flat", "PGSD_B200_SLOT_CSTRIDE": "1"}),
+    # timing experiments (wrong results): what each part of the scatter costs, flat layout
+    ("dbg4 staging only", {"PGSD_B200_SLOT_LAYOUT": "flat", "PGSD_B200_SLOT_DEBUG": "4"}),
+    ("dbg3 staging + atomics", {"PGSD_B200_SLOT_LAYOUT": "flat", "PGSD_B200_SLOT_DEBUG": "3"}),
+    ("dbg1 staging + records at identity positions", {"PGSD_B200_SLOT_LAYOUT": "flat", "PGSD_B200_SLOT_DEBUG": "1"}),
+    ("dbg2 staging + atomics + records at identity positions", {"PGSD_B200_SLOT_LAYOUT": "flat", "PGSD_B200_SLOT_DEBUG": "2"}),
 ]
 if os.environ.get("TIME_SLOT_ONLY"):
     VARIANTS = [v for v in VARIANTS if any(w in v[0] for w in os.environ["TIME_SLOT_ONLY"].split(","))]
