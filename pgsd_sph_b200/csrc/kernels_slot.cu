@@ -36,7 +36,10 @@
 // places) -- additive although no unit is above 35 % busy in ncu: DRAM spends its time opening rows for the
 // write-backs, not transferring.  Tried without gain: a persistent double-buffered variant that overlaps
 // TMA, atomics and stores inside the CTA (0.55 ms), L2 evict-first loads (0.57 ms), packed / 32-byte /
-// 256-byte cursor strides (+-3 %), tiles of 512 / 2048 rows (+-5 %).
+// 256-byte cursor strides (+-3 %), tiles of 512 / 2048 rows (+-5 %); and a separate kernel that only takes the
+// positions (keys -> atomics -> 4 bytes per row; 0.16 ms = the L2's ~100 G atomics/s) with an atomic-free
+// scatter after it: 0.82 ms, because records then no longer arrive in position order and half-filled lines
+// are evicted and fetched again (DRAM 1.34 GB read / 0.99 GB written instead of 0.74 / 0.67).
 //
 // sm_100a only (cp.async.bulk + mbarrier).  No CPU fallback.
 #include "device_internal.h"
