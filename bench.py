@@ -346,11 +346,12 @@ def run_read_leg(lib, dist, args, peaks, windows):
     slot = os.environ.get("PGSD_B200_SLOT", "1") != "0" and phase_ms[2] < 0.02   # unique ids: no pair passes ran
     if slot:
         kernels = {
-            "k4_digit_census": kern(phase_ms[0], 4, "keys read once; includes the 8 KB D2H + host sync"),
             "k6_slot_hist+scan+scatter": kern(phase_ms[1], 4 + 2 * 40, "bucket histogram (4 B) + rows moved once into "
                                               "interleaved records: 40 B read + 40 B written (one cursor atomic per row)"),
             "k6_slot_place": kern(phase_ms[3], 2 * 40, "one CTA per bucket: 40 B records read, 40 B of fields written"),
         }
+        if phase_ms[0] > 0.005:   # the key range guessed from n was wrong: the census measured it
+            kernels["k4_digit_census"] = kern(phase_ms[0], 4, "keys read once (OR/AND); includes the 8-byte D2H + host sync")
     else:
         kernels = {
             "k4_digit_census": kern(phase_ms[0], 4, "keys read once; includes the 8 KB D2H + host sync"),

@@ -18,7 +18,8 @@ int dev_reorder_rows(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, ui
 // kernels_slot.cu: reorder for unique keys; *done = 0 -> not applicable / duplicates, run the general path
 void slot_release_workspace();
 int dev_reorder_slot(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, uint32_t* perm, int nfields,
-                     const ReorderField* fields, int topbit, void* stream, int* done, void (*mark)(int, cudaStream_t));
+                     const ReorderField* fields, int topbit, int guessed, void* stream, int* done, int* out_of_range,
+                     void (*mark)(int, cudaStream_t));
 
 // pgsd_type codes (include/pgsd.h; ref: /root/reference/pgsd/pgsd/pgsd.h:38-69)
 enum : int

@@ -122,12 +122,14 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity)
         }
     }
 
-// flag words (device): [0] set by k6_slot_scan: a bucket holds more than CAP keys (duplicate ids)
+// flag words (device): [2] set by k6_slot_hist: a key lies outside the range guessed from n
+//                      [0] set by k6_slot_scan: [2], or a bucket holds more than CAP keys (duplicate ids)
 //                      [1] set by k6_slot_place: 1 = two rows of a bucket share a slot (duplicate ids),
 //                          3 = a bulk copy never arrived
 // ---- bucket histogram ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) k6_slot_hist(const uint32_t* __restrict__ keys, uint64_t n, int L, uint32_t bmask,
-                                                    uint32_t nb, uint32_t* __restrict__ counts)
+                                                    uint32_t nb, uint32_t high_mask, uint32_t* __restrict__ counts,
+                                                    uint32_t* __restrict__ flag)
     {
     extern __shared__ uint32_t hist[];
     for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x)
@@ -135,9 +137,11 @@ __global__ void __launch_bounds__(1024) k6_slot_hist(const uint32_t* __restrict_
     __syncthreads();
     const uint64_t n4 = n / 4;
     const uint4* k4 = reinterpret_cast<const uint4*>(keys);
+    uint32_t high = 0; // key bits above the assumed range (high_mask != 0: the range was guessed from n, not measured)
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (uint64_t)gridDim.x * blockDim.x)
         {
         const uint4 v = __ldg(k4 + i);
+        high |= v.x | v.y | v.z | v.w;
         atomicAdd(&hist[(v.x >> L) & bmask], 1u);
         atomicAdd(&hist[(v.y >> L) & bmask], 1u);
         atomicAdd(&hist[(v.z >> L) & bmask], 1u);
@@ -145,7 +149,13 @@ __global__ void __launch_bounds__(1024) k6_slot_hist(const uint32_t* __restrict_
         }
     if (blockIdx.x == 0)
         for (uint64_t i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x)
-            atomicAdd(&hist[(keys[i] >> L) & bmask], 1u);
+            {
+            const uint32_t k = keys[i];
+            high |= k;
+            atomicAdd(&hist[(k >> L) & bmask], 1u);
+            }
+    if (high & high_mask)
+        flag[2] = 1;
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x)
         {
@@ -156,28 +166,34 @@ __global__ void __launch_bounds__(1024) k6_slot_hist(const uint32_t* __restrict_
     }
 
 // ---- exclusive scan of <= 32768 bucket counts, one CTA ---------------------------------------------------
-// Thread t owns the `per` consecutive buckets from t * per; its counts are fetched with independent loads
-// (one memory latency for the whole table) and kept in registers for the second sweep.
-constexpr int SCAN_MAX_PER = (1 << SLOT_MAX_BUCKET_BITS) / 1024;
+// Global accesses are coalesced (counts in, bases out, through shared memory); thread t scans the `per`
+// consecutive buckets from t * per in between.  cursor == NULL: the cursors were zeroed by a memset
+// ("lines" layout: positions are relative to the bucket).
 __global__ void __launch_bounds__(1024) k6_slot_scan(const uint32_t* __restrict__ counts, uint32_t nb, uint32_t cap,
                                                     uint32_t n, uint32_t* __restrict__ base, uint32_t* __restrict__ cursor,
-                                                    uint32_t cstride, int zero_cursors, uint32_t* __restrict__ flag)
+                                                    uint32_t cstride, uint32_t* __restrict__ flag)
     {
+    extern __shared__ uint32_t sc[]; // nb + nb / 32 (one pad word per 32: the per-thread chunks start 16 or 32 words apart)
     __shared__ uint32_t wsum[32];
     __shared__ uint32_t over;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    for (uint32_t i = tid; i < nb; i += 1024)
+        sc[i + (i >> 5)] = __ldg(counts + i);
+    if (tid == 0)
+        over = 0;
+    __syncthreads();
     const uint32_t per = (nb + 1023u) / 1024u;
     const uint32_t b0 = (uint32_t)tid * per;
-    uint32_t c[SCAN_MAX_PER];
-#pragma unroll
-    for (int i = 0; i < SCAN_MAX_PER; i++)
-        c[i] = ((uint32_t)i < per && b0 + i < nb) ? __ldg(counts + b0 + i) : 0u;
     uint32_t s = 0, mx = 0;
-#pragma unroll
-    for (int i = 0; i < SCAN_MAX_PER; i++)
+    for (uint32_t i = 0; i < per; i++)
         {
-        s += c[i];
-        mx = c[i] > mx ? c[i] : mx;
+        const uint32_t b = b0 + i;
+        if (b < nb)
+            {
+            const uint32_t c = sc[b + (b >> 5)];
+            s += c;
+            mx = c > mx ? c : mx;
+            }
         }
     uint32_t inc = s;
 #pragma unroll
@@ -189,8 +205,6 @@ __global__ void __launch_bounds__(1024) k6_slot_scan(const uint32_t* __restrict_
         }
     if (lane == 31)
         wsum[w] = inc;
-    if (tid == 0)
-        over = 0;
     __syncthreads();
     if (w == 0)
         {
@@ -209,19 +223,30 @@ __global__ void __launch_bounds__(1024) k6_slot_scan(const uint32_t* __restrict_
     if (mx > cap)
         over = 1;
     uint32_t run = wsum[w] + inc - s;
-#pragma unroll
-    for (int i = 0; i < SCAN_MAX_PER; i++)
-        if ((uint32_t)i < per && b0 + i < nb)
+    for (uint32_t i = 0; i < per; i++)
+        {
+        const uint32_t b = b0 + i;
+        if (b < nb)
             {
-            base[b0 + i] = run;
-            cursor[(size_t)(b0 + i) * cstride] = zero_cursors ? 0u : run;
-            run += c[i];
+            const uint32_t c = sc[b + (b >> 5)];
+            sc[b + (b >> 5)] = run;
+            run += c;
             }
-    if (tid == 0)
-        base[nb] = n;
+        }
     __syncthreads();
-    if (tid == 0 && over)
-        flag[0] = 1;
+    for (uint32_t i = tid; i < nb; i += 1024)
+        {
+        const uint32_t v = sc[i + (i >> 5)];
+        base[i] = v;
+        if (cursor)
+            cursor[(size_t)i * cstride] = v;
+        }
+    if (tid == 0)
+        {
+        base[nb] = n;
+        if (over || flag[2] != 0)
+            flag[0] = 1;
+        }
     }
 
 // records out: a group of lanes writes one record (consecutive words), G records per warp store
@@ -660,13 +685,17 @@ static cudaError_t launch_scatter(uint64_t n, uint32_t tile_first, uint32_t tile
     return cudaGetLastError();
     }
 
-// Tries the slot path.  *done = 1: outputs are complete (stream-ordered work finished; the flag was read
+// Tries the slot path.  topbit: the keys differ only in bits [0, topbit) -- measured by the census, or
+// (guessed != 0) assumed from n for dense ids and verified by k6_slot_hist: *out_of_range = 1 reports a miss.
+// *done = 1: outputs are complete (stream-ordered work finished; the flag was read
 // back).  *done = 0: not applicable or duplicate keys found -- the caller must run the general path (inputs
 // are untouched).  phase: optional cudaEvent_t[2] recorded after the scatter and after the placement.
 int dev_reorder_slot(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, uint32_t* perm, int nfields,
-                     const ReorderField* fields, int topbit, void* stream_v, int* done, void (*mark)(int, cudaStream_t))
+                     const ReorderField* fields, int topbit, int guessed, void* stream_v, int* done, int* out_of_range,
+                     void (*mark)(int, cudaStream_t))
     {
     *done = 0;
+    *out_of_range = 0;
     const char* en = getenv("PGSD_B200_SLOT");
     if (en && en[0] == '0')
         return 0;
@@ -792,6 +821,7 @@ int dev_reorder_slot(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, ui
     if (!attr_done)
         {
         cudaFuncSetAttribute(k6_slot_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << SLOT_MAX_BUCKET_BITS) * 4);
+        cudaFuncSetAttribute(k6_slot_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, ((1 << SLOT_MAX_BUCKET_BITS) / 32 * 33 + 1) * 4);
         cudaFuncSetAttribute(k6_slot_place, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         attr_done = true;
         }
@@ -800,8 +830,11 @@ int dev_reorder_slot(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, ui
     const uint64_t want = (n / 4 + 1023) / 1024;
     if ((uint64_t)hgrid > want)
         hgrid = want ? (int)want : 1;
-    k6_slot_hist<<<hgrid, 1024, (size_t)nb * 4, st>>>(keys, n, L, bmask, nb, counts);
-    k6_slot_scan<<<1, 1024, 0, st>>>(counts, nb, cap, (uint32_t)n, base, cursor, cstride, lines ? 1 : 0, flag);
+    const uint32_t high_mask = (guessed && topbit < 32) ? ~((1u << topbit) - 1u) : 0u;
+    k6_slot_hist<<<hgrid, 1024, (size_t)nb * 4, st>>>(keys, n, L, bmask, nb, high_mask, counts, flag);
+    if (lines)
+        cudaMemsetAsync(cursor, 0, (size_t)nb * cstride * 4, st);
+    k6_slot_scan<<<1, 1024, (size_t)(nb + nb / 32 + 1) * 4, st>>>(counts, nb, cap, (uint32_t)n, base, lines ? nullptr : cursor, cstride, flag);
     dev_stats().kernel_launches += 2;
     cudaError_t e = cudaGetLastError();
     const uint32_t tiles_all = (uint32_t)((n + tile - 1) / tile);
@@ -829,7 +862,7 @@ int dev_reorder_slot(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, ui
         set_last_error(std::string("reorder slot path launch: ") + cudaGetErrorString(e));
         return -1;
         }
-    cudaMemcpyAsync(g_slot_flag_host, flag, 8, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(g_slot_flag_host, flag, 12, cudaMemcpyDeviceToHost, st);
     e = cudaStreamSynchronize(st);
     if (e != cudaSuccess)
         {
@@ -842,6 +875,7 @@ int dev_reorder_slot(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, ui
         return -1;
         }
     *done = (g_slot_flag_host[0] == 0 && g_slot_flag_host[1] == 0) ? 1 : 0;
+    *out_of_range = g_slot_flag_host[2] != 0 ? 1 : 0;
     if (a.debug)
         *done = 1; // timing experiments: the (wrong) result is kept
     return 0;

@@ -6,8 +6,9 @@
 // (/root/reference/pgsd/pgsd/hoomd.py:724-902 never sorts; README.md:29).
 //
 // Pipeline of pgsd_b200_reorder_device (dev_reorder_rows below):
-//   census     k4_digit_census: the four byte histograms of the keys in one read; constant bytes
-//              are skipped, the highest varying bit selects the bucket digit.
+//   census     k4_digit_census: OR and AND of all keys in one streaming read -> which key bytes vary
+//              (constant bytes are skipped) and the highest varying bit, which selects the bucket digit.
+//              Unique ids then take the slot path of kernels_slot.cu; what follows is the general path.
 //   bucket     k4_bucket_aos: stable partition of WHOLE ROWS by the top 8 significant key bits into
 //              one interleaved copy -- afterwards the output rows of a bucket and their source rows
 //              occupy the same index range, so the final gather is local to a few MB (L2) instead of
@@ -72,48 +73,37 @@ __device__ __forceinline__ uint4 ldg_stream_v4(const uint4* p)
     return v;
     }
 
-// ---- pre-pass: four global 256-bin histograms (one per key byte) ------------------------------
+// ---- pre-pass: which key bits vary (OR and AND of all keys; bits 1 in OR and 0 in AND differ somewhere) ----
+// out[0] |= OR, out[1] &= AND.  Pure streaming read; replaces four 256-bin byte histograms (the plan only
+// ever asked which bytes vary and where the highest varying bit is).
 __global__ void __launch_bounds__(512) k4_digit_census(const uint32_t* __restrict__ keys, uint64_t n,
-                                                      unsigned long long* __restrict__ census)
+                                                      uint32_t* __restrict__ out)
     {
-    __shared__ unsigned int h[4][RADIX];
-    for (int i = threadIdx.x; i < 4 * RADIX; i += blockDim.x)
-        (&h[0][0])[i] = 0;
-    __syncthreads();
+    uint32_t o = 0u, a = 0xffffffffu;
     const uint64_t n4 = n / 4;
     const uint4* k4 = reinterpret_cast<const uint4*>(keys);
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
          i += (uint64_t)gridDim.x * blockDim.x)
         {
-        uint4 v;
-        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                     : "l"(k4 + i));
-        uint32_t a[4] = { v.x, v.y, v.z, v.w };
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-            {
-            atomicAdd(&h[0][a[j] & 255u], 1u);
-            atomicAdd(&h[1][(a[j] >> 8) & 255u], 1u);
-            atomicAdd(&h[2][(a[j] >> 16) & 255u], 1u);
-            atomicAdd(&h[3][a[j] >> 24], 1u);
-            }
+        const uint4 v = ldg_stream_v4(k4 + i);
+        o |= v.x | v.y | v.z | v.w;
+        a &= v.x & v.y & v.z & v.w;
         }
     if (blockIdx.x == 0)
         for (uint64_t i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x)
             {
-            uint32_t a = keys[i];
-            atomicAdd(&h[0][a & 255u], 1u);
-            atomicAdd(&h[1][(a >> 8) & 255u], 1u);
-            atomicAdd(&h[2][(a >> 16) & 255u], 1u);
-            atomicAdd(&h[3][a >> 24], 1u);
+            const uint32_t k = keys[i];
+            o |= k;
+            a &= k;
             }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 4 * RADIX; i += blockDim.x)
+    o = __reduce_or_sync(0xffffffffu, o);
+    a = __reduce_and_sync(0xffffffffu, a);
+    if ((threadIdx.x & 31) == 0)
         {
-        unsigned int c = (&h[0][0])[i];
-        if (c)
-            atomicAdd(census + i, (unsigned long long)c);
+        if (o != 0u)
+            atomicOr(out, o);
+        if (a != 0xffffffffu)
+            atomicAnd(out + 1, a);
         }
     }
 
@@ -1385,7 +1375,7 @@ static PassTables pass_tables_at(unsigned char* p, uint64_t n)
     return t;
     }
 
-// Census of the four key bytes (one host round trip): which bytes vary, and the bit length of the
+// Census of the key bits (one host round trip): which bytes vary, and the bit length of the
 // varying part.  passes[] lists the varying bytes, least significant first.
 struct KeyPlan
     {
@@ -1395,41 +1385,38 @@ struct KeyPlan
     };
 static int key_census(uint64_t n, const uint32_t* keys, const PassTables& t, cudaStream_t st, KeyPlan* plan)
     {
-    cudaMemsetAsync(t.census, 0, 4 * RADIX * 8, st);
+    uint32_t* bits = reinterpret_cast<uint32_t*>(t.census);
+    cudaMemsetAsync(bits, 0, 4, st);
+    cudaMemsetAsync(bits + 1, 0xff, 4, st);
     int census_grid = dev_sm_count() * 4;
     uint64_t want = (n / 4 + 511) / 512;
     if ((uint64_t)census_grid > want)
         census_grid = want ? (int)want : 1;
-    k4_digit_census<<<census_grid, 512, 0, st>>>(keys, n, t.census);
+    k4_digit_census<<<census_grid, 512, 0, st>>>(keys, n, bits);
     dev_stats().kernel_launches++;
-    cudaMemcpyAsync(g_census_host, t.census, 4 * RADIX * 8, cudaMemcpyDeviceToHost, st);
+    uint32_t* host = reinterpret_cast<uint32_t*>(g_census_host);
+    cudaMemcpyAsync(host, bits, 8, cudaMemcpyDeviceToHost, st);
     if (cudaStreamSynchronize(st) != cudaSuccess)
         {
         set_last_error(std::string("sort_ids census: ") + cudaGetErrorString(cudaGetLastError()));
         return -1;
         }
+    const uint32_t varying = host[0] & ~host[1];
     plan->npass = 0;
     plan->topbit = 0;
     for (int b = 0; b < 4; b++)
         {
-        int lo = -1, hi = -1;
-        for (int d = 0; d < RADIX; d++)
-            if (g_census_host[b * RADIX + d] != 0)
-                {
-                if (lo < 0)
-                    lo = d;
-                hi = d;
-                }
-        if (lo != hi)
+        uint32_t x = (varying >> (8 * b)) & 255u;
+        if (x)
             {
             plan->passes[plan->npass++] = b;
-            int x = lo ^ hi, bits = 0; // digits of this byte agree above bit `bits`
+            int bits_b = 0; // the keys agree on this byte above bit `bits_b`
             while (x)
                 {
-                bits++;
+                bits_b++;
                 x >>= 1;
                 }
-            plan->topbit = 8 * b + bits;
+            plan->topbit = 8 * b + bits_b;
             }
         }
     return 0;
@@ -1623,6 +1610,50 @@ static uint64_t bucket_min_rows()
     return e ? (uint64_t)atoll(e) : (1ull << 20);
     }
 
+// Slot path attempts.  First with the key range GUESSED from n (dense ids 0..n-1: no census, no host round
+// trip before the kernels; k6_slot_hist verifies the guess).  If only the guess was wrong (ids with an offset
+// or gaps), once more with the range the census measures.  Duplicates: *done stays 0, the caller sorts.
+static int reorder_try_slot(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, uint32_t* perm, int nfields,
+                            const ReorderField* fields, void* stream_v, bool timed, int* done)
+    {
+    *done = 0;
+    cudaStream_t st = (cudaStream_t)stream_v;
+    int rc, miss = 0;
+    const char* eg = getenv("PGSD_B200_SLOT_GUESS");
+    if (n >= 2 && !(eg && eg[0] == '0'))
+        {
+        int tg = 0;
+        while (tg < 32 && ((n - 1) >> tg) != 0)
+            tg++;
+        if (timed)
+            {
+            phase_mark(0, st);
+            phase_mark(1, st);
+            }
+        if ((rc = dev_reorder_slot(n, keys, keys_sorted, perm, nfields, fields, tg, 1, stream_v, done, &miss, timed ? slot_mark : nullptr)) != 0)
+            return rc;
+        if (*done || !miss)
+            return 0; // finished, or not applicable / duplicates: a measured range would not change that
+        }
+    if ((rc = sort_setup()) != 0)
+        return rc;
+    void* ws = nullptr;
+    const size_t arr = align_up((size_t)n * 4, 256);
+    if ((rc = ws_reserve(g_sort_ws, 4 * arr + pass_tables_bytes(n), &ws)) != 0)
+        return rc;
+    const PassTables t = pass_tables_at((unsigned char*)ws + 4 * arr, n);
+    KeyPlan plan;
+    if (timed)
+        phase_mark(0, st);
+    if ((rc = key_census(n, keys, t, st, &plan)) != 0)
+        return rc;
+    if (timed)
+        phase_mark(1, st);
+    if (plan.npass == 0)
+        return 0; // all keys equal: the caller's identity path
+    return dev_reorder_slot(n, keys, keys_sorted, perm, nfields, fields, plan.topbit, 0, stream_v, done, &miss, timed ? slot_mark : nullptr);
+    }
+
 static uint64_t slot_min_rows()
     {
     const char* e = getenv("PGSD_B200_SLOT_MIN_ROWS");
@@ -1658,26 +1689,14 @@ int dev_reorder_rows(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, ui
         }
     if (!rows_ok || n < bucket_min_rows())
         {
-        // small frames with unique ids: the slot path (kernels_slot.cu) is 5 launches instead of ~10
+        // small frames with unique ids: the slot path (kernels_slot.cu) is 4-5 launches instead of ~10
         if (rows_ok && n >= slot_min_rows())
             {
-            if ((rc = sort_setup()) != 0)
+            int done = 0;
+            if ((rc = reorder_try_slot(n, keys, keys_sorted, perm, nfields, fields, stream_v, false, &done)) != 0)
                 return rc;
-            void* ws = nullptr;
-            if ((rc = ws_reserve(g_sort_ws, 4 * align_up((size_t)n * 4, 256) + pass_tables_bytes(n), &ws)) != 0)
-                return rc;
-            const PassTables t = pass_tables_at((unsigned char*)ws + 4 * align_up((size_t)n * 4, 256), n);
-            KeyPlan plan;
-            if ((rc = key_census(n, keys, t, st, &plan)) != 0)
-                return rc;
-            if (plan.npass > 0)
-                {
-                int done = 0;
-                if ((rc = dev_reorder_slot(n, keys, keys_sorted, perm, nfields, fields, plan.topbit, stream_v, &done, nullptr)) != 0)
-                    return rc;
-                if (done)
-                    return 0;
-                }
+            if (done)
+                return 0;
             }
         // small or oddly shaped frames: pair sort + gather from the caller's arrays
         uint32_t* p = perm;
@@ -1702,6 +1721,15 @@ int dev_reorder_rows(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, ui
     uint32_t* kbuf[2] = { (uint32_t*)p, (uint32_t*)(p + arr) };
     uint32_t* ibuf[2] = { (uint32_t*)(p + 2 * arr), (uint32_t*)(p + 3 * arr) };
     const PassTables t = pass_tables_at(p + 4 * arr, n);
+    // unique ids (the normal case): two passes over the rows, no ranking (kernels_slot.cu); duplicates are
+    // detected on the device and fall through to the stable general path below
+        {
+        int done = 0;
+        if ((rc = reorder_try_slot(n, keys, keys_sorted, perm, nfields, fields, stream_v, true, &done)) != 0)
+            return rc;
+        if (done)
+            return 0;
+        }
     KeyPlan plan;
     phase_mark(0, st);
     if ((rc = key_census(n, keys, t, st, &plan)) != 0)
@@ -1719,15 +1747,6 @@ int dev_reorder_rows(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, ui
         for (int i = 0; i < nfields; i++)
             cudaMemcpyAsync(fields[i].out, fields[i].in, n * (size_t)fields[i].row_bytes, cudaMemcpyDeviceToDevice, st);
         return cudaGetLastError() == cudaSuccess ? 0 : -1;
-        }
-    // unique ids (the normal case): two passes over the rows, no ranking (kernels_slot.cu); duplicates are
-    // detected on the device and fall through to the stable general path below
-        {
-        int done = 0;
-        if ((rc = dev_reorder_slot(n, keys, keys_sorted, perm, nfields, fields, plan.topbit, stream_v, &done, slot_mark)) != 0)
-            return rc;
-        if (done)
-            return 0;
         }
     const bool direct = plan.npass == 1; // one varying byte: the bucket pass is the whole sort
     uint32_t row_words = perm ? 1u : 0u;

@@ -347,7 +347,9 @@ def _launches(lib):
     return int(st.kernel_launches)
 
 
-SLOT_LAUNCHES = (5,)   # census + histogram + scan + scatter + place; more = the general path ran
+# histogram + scan + scatter + place with the key range guessed from n; a wrong guess (ids with offset or gaps)
+# costs that attempt + census + the four kernels again; anything more = the general path ran
+SLOT_LAUNCHES = (4, 9)
 
 
 def slot_key_cases():
@@ -365,6 +367,7 @@ def slot_key_cases():
     yield "sparse_unique", rng.choice(1 << 22, size=150001, replace=False).astype(np.uint32), True
     yield "const_high_bits", (rng.permutation(50000) + 0xABC00000).astype(np.uint32), True
     yield "gaps_and_offset", (rng.permutation(40000) * 3 + 77777).astype(np.uint32), True
+    yield "dense_with_offset_1", (rng.permutation(65536) + 1).astype(np.uint32), True   # one key just outside the guessed range
     yield "one_dup_pair", np.concatenate([rng.permutation(90000), [4242]]).astype(np.uint32), False
     yield "dups_2bytes", rng.integers(0, 40000, size=123457).astype(np.uint32), False  # bucket overflow -> flag in the scan
     yield "dups_low_density", rng.integers(0, 1 << 22, size=100000).astype(np.uint32), False  # dups found by the placement
