@@ -157,6 +157,21 @@ int pgsd_b200_reorder_host(uint64_t n, const uint32_t* keys_host, uint32_t* keys
                            uint32_t* perm_host, int nfields,
                            const struct pgsd_b200_field* fields_host);
 
+/* K4+K5 for ONE frame whose rows are partitioned over the ranks (one process per GPU; SURVEY.md section 8e,
+   config 3 read-back: rank r has read file partition r -- pgsd_read_chunk(..., all=true), pgsd.c:2497-2508 --
+   and the frame must come out in particle-id order).  Collective over the communicator, at most 8 ranks.
+   Rank r ends up with the rows whose ids lie in [*id_first, *id_first + S), S = ceil(ceil(N / C) / ranks) * C
+   with C = 1024 (2048 / 4096 for more than 32 Mi / 64 Mi rows in total), in id order: *n_out rows written to
+   keys_sorted_device and to every fields[i].out (capacity out_capacity rows each; S always suffices).
+   The exchange is not a separate step: the scatter kernel stores every record straight into the owner's
+   memory (CUDA IPC mapping, i.e. NVLink) and the owner finishes its buckets locally.
+   Returns 0, a negative pgsd error, or 1 on EVERY rank when the ids are not unique or not all below
+   ceil(N / C) * C (dense ids 0..N-1 qualify): nothing was written, gather the frame to one GPU and use
+   pgsd_b200_reorder_device.  row_bytes must be multiples of 4; keys 16-byte aligned. */
+int pgsd_b200_reorder_distributed(uint64_t n_local, const uint32_t* keys_device, uint64_t out_capacity,
+                                  uint64_t* n_out, uint64_t* id_first, uint32_t* keys_sorted_device,
+                                  int nfields, const struct pgsd_b200_field* fields_device, void* cuda_stream);
+
 /* ------------------------------------------------------------------ accounting */
 struct pgsd_b200_stats
     {

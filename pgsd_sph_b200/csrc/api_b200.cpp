@@ -281,6 +281,18 @@ int pgsd_b200_reorder_host(uint64_t n, const uint32_t* keys_host, uint32_t* keys
     return dev_reorder_host(n, keys_host, keys_sorted_host, perm_host, nfields, f.data());
     }
 
+int pgsd_b200_reorder_distributed(uint64_t n_local, const uint32_t* keys_device, uint64_t out_capacity,
+                                  uint64_t* n_out, uint64_t* id_first, uint32_t* keys_sorted_device,
+                                  int nfields, const struct pgsd_b200_field* fields_device, void* cuda_stream)
+    {
+    std::vector<ReorderField> f;
+    int rc = to_fields(nfields, fields_device, f);
+    if (rc != 0)
+        return rc;
+    return dev_reorder_distributed(n_local, keys_device, out_capacity, n_out, id_first, keys_sorted_device, nfields,
+                                   f.data(), cuda_stream);
+    }
+
 // ------------------------------------------------------------------ accounting
 int pgsd_b200_get_stats(struct pgsd_b200_stats* out)
     {

@@ -96,6 +96,10 @@ int dev_reorder(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, uint32_
                 const ReorderField* fields, void* stream);
 int dev_reorder_host(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, uint32_t* perm,
                      int nfields, const ReorderField* fields);
+// one frame partitioned over the ranks (kernels_slot.cu); 1 = ids not unique / not dense, nothing written
+int dev_reorder_distributed(uint64_t n_local, const uint32_t* keys, uint64_t out_capacity, uint64_t* n_out,
+                            uint64_t* id_first, uint32_t* keys_sorted, int nfields, const ReorderField* fields,
+                            void* stream);
 
 // phase timing of the last bucketed reorder (CUDA events): census, bucket pass, pair passes, gather
 void dev_pack_profiling(bool on); // K1 launch of the last frame write

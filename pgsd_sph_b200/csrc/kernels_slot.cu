@@ -44,7 +44,10 @@
 // sm_100a only (cp.async.bulk + mbarrier).  No CPU fallback.
 #include "device_internal.h"
 
+#include "comm.h"
+
 #include <cstdlib>
+#include <vector>
 
 namespace pgsdb
 {
@@ -73,6 +76,11 @@ struct SlotArgs
                   // bucket b lives at line j * nb + b, so that the lines the buckets are currently filling (about the
                   // same j for all of them) form one compact, advancing window instead of nb windows spread over the
                   // whole copy: the L2 write-backs then fall into few open DRAM rows
+    // distributed reorder: rank `o` owns the buckets [o * nbr, (o + 1) * nbr); peer[o] is its interleaved copy
+    // (own memory, or a CUDA IPC mapping of the owner's memory: the record stores then travel over NVLink)
+    uint32_t* peer[8];
+    uint32_t nbr;
+    int nranks; // 1: single-GPU reorder, peer[] unused
     int debug; // timing experiments only (results are wrong): 1 = no atomics, identity positions; 2 = atomics, identity
                // positions; 3 = atomics, nothing written; 4 = staging only
     };
@@ -128,8 +136,8 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity)
 //                          3 = a bulk copy never arrived
 // ---- bucket histogram ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) k6_slot_hist(const uint32_t* __restrict__ keys, uint64_t n, int L, uint32_t bmask,
-                                                    uint32_t nb, uint32_t high_mask, uint32_t* __restrict__ counts,
-                                                    uint32_t* __restrict__ flag)
+                                                    uint32_t nb, uint32_t high_mask, uint32_t key_limit,
+                                                    uint32_t* __restrict__ counts, uint32_t* __restrict__ flag)
     {
     extern __shared__ uint32_t hist[];
     for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x)
@@ -138,10 +146,12 @@ __global__ void __launch_bounds__(1024) k6_slot_hist(const uint32_t* __restrict_
     const uint64_t n4 = n / 4;
     const uint4* k4 = reinterpret_cast<const uint4*>(keys);
     uint32_t high = 0; // key bits above the assumed range (high_mask != 0: the range was guessed from n, not measured)
+    uint32_t kmax = 0; // largest key (key_limit != 0: ids must be < key_limit, distributed reorder)
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (uint64_t)gridDim.x * blockDim.x)
         {
         const uint4 v = __ldg(k4 + i);
         high |= v.x | v.y | v.z | v.w;
+        kmax = max(max(kmax, max(v.x, v.y)), max(v.z, v.w));
         atomicAdd(&hist[(v.x >> L) & bmask], 1u);
         atomicAdd(&hist[(v.y >> L) & bmask], 1u);
         atomicAdd(&hist[(v.z >> L) & bmask], 1u);
@@ -152,9 +162,10 @@ __global__ void __launch_bounds__(1024) k6_slot_hist(const uint32_t* __restrict_
             {
             const uint32_t k = keys[i];
             high |= k;
+            kmax = max(kmax, k);
             atomicAdd(&hist[(k >> L) & bmask], 1u);
             }
-    if (high & high_mask)
+    if ((high & high_mask) || (key_limit != 0 && kmax >= key_limit))
         flag[2] = 1;
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x)
@@ -289,8 +300,9 @@ __device__ __forceinline__ void slot_records_out(const uint32_t* __restrict__ ra
                         if (args.nbl)
                             {
                             const uint32_t o = (dd[u] & 4095u) * (RW * 4u) + c2 * 8u;
-                            const uint64_t at = ((uint64_t)((o >> 7) * args.nbl + (dd[u] >> 12)) << 7) + (o & 127u);
-                            *reinterpret_cast<uint2*>(reinterpret_cast<unsigned char*>(aos) + at) = v[u];
+                            const uint64_t at = ((uint64_t)((o >> 7) * args.nbl + ((dd[u] >> 12) & 32767u)) << 7) + (o & 127u);
+                            unsigned char* copy = reinterpret_cast<unsigned char*>(args.nranks > 1 ? args.peer[dd[u] >> 27] : aos);
+                            *reinterpret_cast<uint2*>(copy + at) = v[u];
                             }
                         else
                             aos2[(uint64_t)dd[u] * R2 + c2] = v[u];
@@ -327,8 +339,9 @@ __device__ __forceinline__ void slot_records_out(const uint32_t* __restrict__ ra
                         if (args.nbl)
                             {
                             const uint32_t o = (dd[u] & 4095u) * (RW * 4u) + c * 4u;
-                            const uint64_t at = ((uint64_t)((o >> 7) * args.nbl + (dd[u] >> 12)) << 7) + (o & 127u);
-                            *reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(aos) + at) = v[u];
+                            const uint64_t at = ((uint64_t)((o >> 7) * args.nbl + ((dd[u] >> 12) & 32767u)) << 7) + (o & 127u);
+                            unsigned char* copy = reinterpret_cast<unsigned char*>(args.nranks > 1 ? args.peer[dd[u] >> 27] : aos);
+                            *reinterpret_cast<uint32_t*>(copy + at) = v[u];
                             }
                         else
                             aos[(uint64_t)dd[u] * RW + c] = v[u];
@@ -440,7 +453,16 @@ __global__ void __launch_bounds__(NT) k6_slot_scatter(uint64_t n, uint32_t tile_
                 const uint32_t b = (key[k] >> L) & bmask;
                 d[k] = atomicAdd(cursor + (size_t)b * cstride, 1u);
                 if (args.nbl)
-                    d[k] |= b << 12; // position inside the bucket (< 4096) and the bucket
+                    {
+                    // position inside the bucket (< 4096), the bucket (< 32768) and, distributed, its owner
+                    uint32_t owner = 0, bl = b;
+                    if (args.nranks > 1)
+                        {
+                        owner = b / args.nbr;
+                        bl = b - owner * args.nbr;
+                        }
+                    d[k] = (d[k] & 4095u) | (bl << 12) | (owner << 27);
+                    }
                 if (args.debug == 2 || args.debug == 3)
                     d[k] = (uint32_t)(tile0 + r) + (d[k] >> 31);
                 }
@@ -638,6 +660,13 @@ __global__ void __launch_bounds__(1024) k6_slot_place(const uint32_t* __restrict
                 }
         }
     }
+// cursors of the distributed reorder: cursor[b * cstride] = first position of this rank's records in bucket b
+__global__ void k6_slot_spread(const uint32_t* __restrict__ start, uint32_t nb, uint32_t* __restrict__ cursor, uint32_t cstride)
+    {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < nb)
+        cursor[(size_t)b * cstride] = start[b];
+    }
     } // namespace
 
 // ---- host side -------------------------------------------------------------------------------------------
@@ -645,8 +674,10 @@ static void* g_slot_ws = nullptr;
 static size_t g_slot_ws_bytes = 0;
 static uint32_t* g_slot_flag_host = nullptr; // pinned, 2 words
 
+void dist_release_workspace();
 void slot_release_workspace()
     {
+    dist_release_workspace();
     if (g_slot_ws)
         cudaFree(g_slot_ws);
     g_slot_ws = nullptr;
@@ -736,6 +767,7 @@ int dev_reorder_slot(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, ui
         return 0;
     a.nfields = nf;
     a.row_words = off;
+    a.nranks = 1;
     const char* eb = getenv("PGSD_B200_SLOT_BULK");
     a.bulk = (aligned && !(eb && eb[0] == '0')) ? 1 : 0;
     const char* ed = getenv("PGSD_B200_SLOT_DEBUG");
@@ -831,7 +863,7 @@ int dev_reorder_slot(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, ui
     if ((uint64_t)hgrid > want)
         hgrid = want ? (int)want : 1;
     const uint32_t high_mask = (guessed && topbit < 32) ? ~((1u << topbit) - 1u) : 0u;
-    k6_slot_hist<<<hgrid, 1024, (size_t)nb * 4, st>>>(keys, n, L, bmask, nb, high_mask, counts, flag);
+    k6_slot_hist<<<hgrid, 1024, (size_t)nb * 4, st>>>(keys, n, L, bmask, nb, high_mask, 0u, counts, flag);
     if (lines)
         cudaMemsetAsync(cursor, 0, (size_t)nb * cstride * 4, st);
     k6_slot_scan<<<1, 1024, (size_t)(nb + nb / 32 + 1) * 4, st>>>(counts, nb, cap, (uint32_t)n, base, lines ? nullptr : cursor, cstride, flag);
@@ -879,5 +911,407 @@ int dev_reorder_slot(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, ui
     if (a.debug)
         *done = 1; // timing experiments: the (wrong) result is kept
     return 0;
+    }
+
+// ---- distributed reorder: ONE frame whose rows are partitioned over the ranks (config 3 read-back) -----------
+// "GPU g loads file partition g; destination GPU = id / ceil(N/G); one all-to-all of
+// 40-byte rows, then local sort + gather".  Here the all-to-all is not a separate step: k6_slot_scatter writes
+// every record straight into the owner's interleaved copy -- its own memory or a CUDA IPC mapping of the peer's,
+// i.e. plain stores over NVLink -- and each owner then runs the unchanged k6_slot_place on its buckets.
+//   1 all-gather  n_local, output capacity, size of the shared copy   (-> geometry, same on every rank)
+//   2 all-gather  IPC handle of the shared copy                       (mappings are cached between calls)
+//   3 k6_slot_hist on the local keys; all-gather of the bucket counts (+ the range flag): every rank now knows
+//     where its records start inside every bucket (sum of the counts of lower ranks: cursors need no remote
+//     atomics), how many rows every rank will own, and whether a bucket overflows -- identical decisions
+//   4 k6_slot_scatter (local atomics, local + remote stores), stream sync, barrier all-gather
+//   5 k6_slot_place on the owned buckets, all-gather of the duplicate flags
+// Requires unique ids below ceil(N / 2^L) * 2^L (dense ids 0..N-1 qualify); otherwise every rank returns 1
+// and the caller gathers the frame to one GPU and uses pgsd_b200_reorder_device.
+static void* g_dist_copy = nullptr; // this rank's part of the interleaved copy (IPC-exported)
+static size_t g_dist_copy_bytes = 0;
+static void* g_dist_peer[8] = { nullptr };
+static cudaIpcMemHandle_t g_dist_peer_handle[8];
+static bool g_dist_peer_open[8] = { false };
+
+static void dist_close_peers()
+    {
+    for (int p = 0; p < 8; p++)
+        {
+        if (g_dist_peer_open[p] && g_dist_peer[p])
+            cudaIpcCloseMemHandle(g_dist_peer[p]);
+        g_dist_peer_open[p] = false;
+        g_dist_peer[p] = nullptr;
+        }
+    }
+
+void dist_release_workspace()
+    {
+    dist_close_peers();
+    if (g_dist_copy)
+        cudaFree(g_dist_copy);
+    g_dist_copy = nullptr;
+    g_dist_copy_bytes = 0;
+    }
+
+int dev_reorder_distributed(uint64_t n_local, const uint32_t* keys, uint64_t out_capacity, uint64_t* n_out, uint64_t* id_first,
+                            uint32_t* keys_sorted, int nfields, const ReorderField* fields, void* stream_v)
+    {
+    int rc = dev_init(-1);
+    if (rc != 0)
+        return rc;
+    Comm* c = comm();
+    const int G = c->nprocs, me = c->rank;
+    if (G > 8)
+        {
+        set_last_error("reorder_distributed: at most 8 ranks");
+        return -2;
+        }
+    if (nfields < 0 || (nfields > 0 && fields == nullptr) || n_out == nullptr || nfields + 1 > SLOT_MAX_FIELDS
+        || (n_local > 0 && keys == nullptr) || ((uintptr_t)keys & 15u) != 0)
+        {
+        set_last_error("reorder_distributed: bad arguments (keys must be 16-byte aligned)");
+        return -2;
+        }
+    cudaStream_t st = (cudaStream_t)stream_v;
+    SlotArgs a;
+    memset(&a, 0, sizeof(a));
+    int nf = 0;
+    uint32_t off = 0, in_words = 0;
+    bool aligned = true;
+    a.f[nf++] = SlotField { keys, keys_sorted, 1u, off };
+    off += 1;
+    in_words += 1;
+    for (int i = 0; i < nfields; i++)
+        {
+        const ReorderField& f = fields[i];
+        if (f.row_bytes == 0 || f.row_bytes % 4 != 0 || (((uintptr_t)f.in | (uintptr_t)f.out) & 3u) != 0
+            || (n_local > 0 && f.in == nullptr) || (out_capacity > 0 && f.out == nullptr))
+            {
+            set_last_error("reorder_distributed: fields must be word sized and word aligned");
+            return -2;
+            }
+        if (((uintptr_t)f.in & 15u) != 0)
+            aligned = false;
+        a.f[nf++] = SlotField { (const uint32_t*)f.in, (uint32_t*)f.out, f.row_bytes / 4, off };
+        off += f.row_bytes / 4;
+        in_words += f.row_bytes / 4;
+        }
+    if (off > SLOT_MAX_ROW_WORDS)
+        {
+        set_last_error("reorder_distributed: rows of at most 31 words");
+        return -2;
+        }
+    a.nfields = nf;
+    a.row_words = off;
+    a.nranks = G;
+    a.bulk = aligned ? 1 : 0;
+
+    // (1) sizes
+    uint64_t mine[3] = { n_local, out_capacity, (uint64_t)g_dist_copy_bytes };
+    std::vector<uint64_t> all((size_t)G * 3);
+    if (c->allgather(mine, all.data(), 3) != 0)
+        return -1;
+    uint64_t N = 0;
+    for (int p = 0; p < G; p++)
+        N += all[(size_t)p * 3];
+    *n_out = 0;
+    if (id_first)
+        *id_first = 0;
+    if (N == 0)
+        return 0;
+    if (N >= 0xffffffffull)
+        {
+        set_last_error("reorder_distributed: fewer than 2^32 - 1 rows in total");
+        return -2;
+        }
+    int tg = 0;
+    while (tg < 32 && ((N - 1) >> tg) != 0)
+        tg++;
+    int L = SLOT_MIN_BITS;
+    while (tg - L > SLOT_MAX_BUCKET_BITS)
+        L++;
+    const size_t place_smem = slot_place_smem(L, a.row_words);
+    if (L > SLOT_MAX_BITS || place_smem > 220 * 1024)
+        {
+        set_last_error("reorder_distributed: frame too large for the slot geometry");
+        return -2;
+        }
+    const uint32_t cap = 1u << L;
+    const uint32_t nbp = 1u << (tg > L ? tg - L : 0); // histogram size (power of two)
+    const uint32_t bmask = nbp - 1u;
+    const uint32_t nb_used = (uint32_t)((N + cap - 1) / cap);
+    const uint32_t nbr = (nb_used + (uint32_t)G - 1) / (uint32_t)G; // buckets per owner
+    const uint64_t key_limit = (uint64_t)nb_used * cap;             // <= 2^27
+    const uint32_t my_b0 = (uint32_t)me * nbr < nb_used ? (uint32_t)me * nbr : nb_used;
+    const uint32_t my_b1 = my_b0 + nbr < nb_used ? my_b0 + nbr : nb_used;
+    if (id_first)
+        *id_first = (uint64_t)me * nbr * cap;
+    a.nbl = nbr;
+    a.nbr = nbr;
+    int tile = 1024;
+    while (tile > 512 && ((size_t)in_words + 1) * tile * 4 > 200 * 1024)
+        tile /= 2;
+
+    // (2) the shared copy: same size on every rank; reallocation is a collective decision
+    const size_t nlines = ((size_t)cap * a.row_words * 4 + 127) / 128;
+    const size_t copy_need = up256((size_t)nbr * nlines * 128) + 256;
+    bool grow = false;
+    for (int p = 0; p < G; p++)
+        if (all[(size_t)p * 3 + 2] < copy_need)
+            grow = true;
+    if (grow)
+        {
+        dist_close_peers();
+        if (cudaStreamSynchronize(st) != cudaSuccess || c->barrier() != 0) // nobody maps the old copies any more
+            return -1;
+        if (g_dist_copy)
+            cudaFree(g_dist_copy);
+        g_dist_copy = nullptr;
+        g_dist_copy_bytes = 0;
+        const bool ok = cudaMalloc(&g_dist_copy, copy_need) == cudaSuccess;
+        if (ok)
+            g_dist_copy_bytes = copy_need;
+        else
+            cudaGetLastError();
+        }
+    uint64_t hsend[9];
+    memset(hsend, 0, sizeof(hsend));
+    cudaIpcMemHandle_t myh;
+    memset(&myh, 0, sizeof(myh));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    hsend[8] = g_dist_copy ? 1 : 0;
+    if (g_dist_copy && G > 1)
+        {
+        if (cudaIpcGetMemHandle(&myh, g_dist_copy) != cudaSuccess)
+            {
+            cudaGetLastError();
+            hsend[8] = 0;
+            }
+        memcpy(hsend, &myh, 64);
+        }
+    std::vector<uint64_t> hall((size_t)G * 9);
+    if (c->allgather(hsend, hall.data(), 9) != 0)
+        return -1;
+    for (int p = 0; p < G; p++)
+        if (hall[(size_t)p * 9 + 8] == 0)
+            {
+            set_last_error("reorder_distributed: a rank could not allocate / export its part of the copy");
+            return -6;
+            }
+    for (int p = 0; p < G; p++)
+        {
+        if (p == me)
+            {
+            a.peer[p] = (uint32_t*)g_dist_copy;
+            continue;
+            }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, &hall[(size_t)p * 9], 64);
+        if (!g_dist_peer_open[p] || memcmp(&h, &g_dist_peer_handle[p], 64) != 0)
+            {
+            if (g_dist_peer_open[p] && g_dist_peer[p])
+                cudaIpcCloseMemHandle(g_dist_peer[p]);
+            g_dist_peer_open[p] = false;
+            void* ptr = nullptr;
+            cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess)
+                {
+                set_last_error(std::string("reorder_distributed: cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+                cudaGetLastError();
+                // keep the collective sequence intact: the failure is reported through the counts all-gather below
+                ptr = nullptr;
+                }
+            g_dist_peer[p] = ptr;
+            g_dist_peer_handle[p] = h;
+            g_dist_peer_open[p] = ptr != nullptr;
+            }
+        a.peer[p] = (uint32_t*)g_dist_peer[p];
+        }
+    bool peers_ok = true;
+    for (int p = 0; p < G; p++)
+        if (a.peer[p] == nullptr)
+            peers_ok = false;
+
+    // local workspace: [flag 256 B][counts nbp][base nbr+1][start nbp][cursors nbp * cstride]
+    const uint32_t cstride = 32;
+    const size_t tb = up256((size_t)(nbp + 1) * 4);
+    const size_t bb = up256((size_t)(nbr + 2) * 4);
+    const size_t cb = up256((size_t)nbp * cstride * 4);
+    const size_t need = 256 + 2 * tb + bb + cb;
+    bool ws_ok = true;
+    if (g_slot_ws_bytes < need)
+        {
+        if (g_slot_ws)
+            cudaFree(g_slot_ws);
+        g_slot_ws = nullptr;
+        g_slot_ws_bytes = 0;
+        if (cudaMalloc(&g_slot_ws, need) != cudaSuccess)
+            {
+            cudaGetLastError();
+            ws_ok = false;
+            }
+        else
+            g_slot_ws_bytes = need;
+        }
+    if (!g_slot_flag_host && cudaHostAlloc((void**)&g_slot_flag_host, 256, cudaHostAllocDefault) != cudaSuccess)
+        {
+        cudaGetLastError();
+        ws_ok = false;
+        }
+    static bool attr_done = false;
+    if (!attr_done)
+        {
+        cudaFuncSetAttribute(k6_slot_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << SLOT_MAX_BUCKET_BITS) * 4);
+        cudaFuncSetAttribute(k6_slot_place, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        attr_done = true;
+        }
+    unsigned char* p8 = (unsigned char*)g_slot_ws;
+    uint32_t* flag = (uint32_t*)p8;
+    uint32_t* counts = (uint32_t*)(p8 + 256);
+    uint32_t* base = (uint32_t*)(p8 + 256 + tb);
+    uint32_t* start = (uint32_t*)(p8 + 256 + tb + bb);
+    uint32_t* cursor = (uint32_t*)(p8 + 256 + 2 * tb + bb);
+
+    // (3) local histogram, counts of all ranks
+    const size_t cw = ((size_t)nbp + 1) / 2 + 1; // u64 words: packed counts + status word
+    std::vector<uint64_t> csend(cw, 0), call((size_t)G * cw);
+    std::vector<uint32_t> hcounts((size_t)nbp + 1, 0);
+    uint64_t status = (ws_ok && peers_ok) ? 0 : 4; // 1: key out of range, 4: resource failure
+    if (ws_ok)
+        {
+        cudaMemsetAsync(p8, 0, 256 + tb, st);
+        if (n_local > 0)
+            {
+            int hgrid = dev_sm_count() * (nbp <= 16384 ? 2 : 1);
+            const uint64_t want = (n_local / 4 + 1023) / 1024;
+            if ((uint64_t)hgrid > want)
+                hgrid = want ? (int)want : 1;
+            k6_slot_hist<<<hgrid, 1024, (size_t)nbp * 4, st>>>(keys, n_local, L, bmask, nbp, 0u, (uint32_t)key_limit, counts, flag);
+            dev_stats().kernel_launches++;
+            }
+        cudaMemcpyAsync(hcounts.data(), counts, (size_t)nbp * 4, cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(g_slot_flag_host, flag, 12, cudaMemcpyDeviceToHost, st);
+        if (cudaStreamSynchronize(st) != cudaSuccess)
+            {
+            cudaGetLastError();
+            status |= 4;
+            }
+        else if (g_slot_flag_host[2] != 0)
+            status |= 1;
+        }
+    memcpy(csend.data(), hcounts.data(), (size_t)nbp * 4);
+    csend[cw - 1] = status;
+    if (c->allgather(csend.data(), call.data(), cw) != 0)
+        return -1;
+    uint64_t any = 0;
+    for (int p = 0; p < G; p++)
+        any |= call[(size_t)p * cw + cw - 1];
+    if (any & 4)
+        {
+        set_last_error("reorder_distributed: a rank failed to allocate or map memory");
+        return -6;
+        }
+    if (any & 1)
+        return 1; // ids outside [0, key_limit): not applicable
+    // where my records start in every bucket, how full every bucket gets, who owns how many rows
+    std::vector<uint32_t> hstart(nbp, 0), hbase((size_t)nbr + 2, 0);
+    std::vector<uint64_t> owned(G, 0);
+    bool overflow = false;
+    for (uint32_t b = 0; b < nbp; b++)
+        {
+        uint32_t tot = 0;
+        for (int p = 0; p < G; p++)
+            {
+            const uint32_t cpb = reinterpret_cast<const uint32_t*>(&call[(size_t)p * cw])[b];
+            if (p == me)
+                hstart[b] = tot;
+            tot += cpb;
+            }
+        if (tot > cap)
+            overflow = true;
+        const uint32_t o = b / nbr;
+        if (b < nb_used && o < (uint32_t)G)
+            {
+            owned[o] += tot;
+            if (o == (uint32_t)me)
+                hbase[b - my_b0 + 1] = tot;
+            }
+        }
+    if (overflow)
+        return 1; // more ids than slots in a bucket: duplicates
+    bool fits = true;
+    for (int p = 0; p < G; p++)
+        if (owned[p] > all[(size_t)p * 3 + 1])
+            fits = false;
+    if (!fits)
+        {
+        set_last_error("reorder_distributed: out_capacity too small on some rank (rows owned: ceil(N / 2^L / ranks) * 2^L at most)");
+        return -2;
+        }
+    for (uint32_t i = 1; i <= nbr; i++) // counts -> exclusive prefix; entries past my last bucket repeat the total
+        hbase[i] += hbase[i - 1];
+    hbase[nbr + 1] = hbase[nbr];
+    *n_out = owned[me];
+    cudaMemcpyAsync(start, hstart.data(), (size_t)nbp * 4, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(base, hbase.data(), (size_t)(nbr + 1) * 4, cudaMemcpyHostToDevice, st);
+    k6_slot_spread<<<(nbp + 255) / 256, 256, 0, st>>>(start, nbp, cursor, cstride);
+    dev_stats().kernel_launches++;
+
+    // (4) records to their owners
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && n_local > 0)
+        {
+        const uint32_t tiles_all = (uint32_t)((n_local + tile - 1) / tile);
+        if (tile == 512)
+            e = launch_scatter<512, 128>(n_local, 0, tiles_all, L, bmask, cursor, cstride, (uint32_t*)g_dist_copy, flag, a, in_words, st);
+        else
+            e = launch_scatter<1024, 256>(n_local, 0, tiles_all, L, bmask, cursor, cstride, (uint32_t*)g_dist_copy, flag, a, in_words, st);
+        }
+    cudaMemcpyAsync(g_slot_flag_host, flag, 12, cudaMemcpyDeviceToHost, st);
+    uint64_t st4 = 0;
+    if (e != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)
+        {
+        set_last_error(std::string("reorder_distributed scatter: ") + cudaGetErrorString(e != cudaSuccess ? e : cudaGetLastError()));
+        st4 = 4;
+        }
+    else if (g_slot_flag_host[1] == 3)
+        st4 = 4;
+    std::vector<uint64_t> sall(G);
+    if (c->allgather(&st4, sall.data(), 1) != 0) // also the barrier: every record has reached its owner
+        return -1;
+    for (int p = 0; p < G; p++)
+        if (sall[p] != 0)
+            {
+            if (st4 == 0)
+                set_last_error("reorder_distributed: the scatter failed on another rank");
+            return -1;
+            }
+
+    // (5) my buckets
+    uint64_t st5 = 0;
+    if (my_b1 > my_b0)
+        {
+        SlotArgs ap = a;
+        ap.bulk = 1;
+        k6_slot_place<<<my_b1 - my_b0, cap / 4, place_smem, st>>>(base, L, (const uint32_t*)g_dist_copy, flag, ap);
+        dev_stats().kernel_launches++;
+        e = cudaGetLastError();
+        cudaMemcpyAsync(g_slot_flag_host, flag, 12, cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)
+            {
+            set_last_error(std::string("reorder_distributed place: ") + cudaGetErrorString(e != cudaSuccess ? e : cudaGetLastError()));
+            st5 = 4;
+            }
+        else if (g_slot_flag_host[1] != 0)
+            st5 = 1; // two records of a bucket share a slot
+        }
+    if (c->allgather(&st5, sall.data(), 1) != 0)
+        return -1;
+    any = 0;
+    for (int p = 0; p < G; p++)
+        any |= sall[p];
+    if (any & 4)
+        return -1;
+    return (any & 1) ? 1 : 0;
     }
 } // namespace pgsdb

@@ -1,0 +1,61 @@
+"""Distributed reorder (pgsd_b200_reorder_distributed, SURVEY.md section 8e: one frame partitioned over the
+ranks): P processes on cuda:0 with the shared-memory communicator; records travel between the processes through
+CUDA IPC mappings exactly as they do between GPUs.  Oracle: numpy stable argsort of the whole frame."""
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import dist_reorder_worker as W
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("nprocs", [1, 2, 3, 4, 8])
+def test_reorder_distributed_equals_stable_argsort(lib, nprocs):
+    assert lib.pgsd_b200_cuda_available() == 1, "no CUDA device: the device path has no CPU fallback"
+    with tempfile.TemporaryDirectory() as d:
+        seg = f"/pgsd_dist_{os.getpid()}_{nprocs}"
+        procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "dist_reorder_worker.py"), str(r), str(nprocs), seg, d],
+                                  stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(nprocs)]
+        outs = []
+        for p in procs:
+            try:
+                o, _ = p.communicate(timeout=300)
+            except subprocess.TimeoutExpired:
+                for q in procs:
+                    q.kill()
+                raise
+            outs.append(o)
+        for r, (p, o) in enumerate(zip(procs, outs)):
+            assert p.returncode == 0, f"rank {r}:\n{o}"
+        for ci, (name, n, gen) in enumerate(W.cases()):
+            rng = np.random.default_rng(1000 + ci)
+            ids = gen(rng, n)
+            pos = rng.standard_normal((n, 3)).astype(np.float32)
+            tag = (ids ^ np.uint32(0x9e3779b9)).astype(np.uint32)
+            dens = rng.standard_normal(n)
+            res = [np.load(os.path.join(d, f"rank{r}_{name}.npz")) for r in range(nprocs)]
+            rcs = {int(x["rc"]) for x in res}
+            assert len(rcs) == 1, (name, rcs)          # a collective decision
+            if name in ("one_dup", "dup_in_partial_bucket", "out_of_range"):
+                assert rcs == {1}, (name, rcs)
+                continue
+            assert rcs == {0}, (name, rcs)
+            o = np.argsort(ids, kind='stable')
+            got_ids = np.concatenate([x["ids"] for x in res])
+            assert got_ids.tobytes() == ids[o].tobytes(), name
+            assert np.concatenate([x["pos"] for x in res]).tobytes() == pos[o].tobytes(), name
+            assert np.concatenate([x["tag"] for x in res]).tobytes() == tag[o].tobytes(), name
+            assert np.concatenate([x["dens"] for x in res]).tobytes() == dens[o].tobytes(), name
+            # ownership: rank r holds exactly the ids of [id_first, id_first of the next rank)
+            for r, x in enumerate(res):
+                if x["n_out"] > 0:
+                    assert x["ids"][0] >= x["id_first"]
+                    if r + 1 < nprocs:
+                        assert x["ids"][-1] < res[r + 1]["id_first"]
