@@ -376,6 +376,75 @@ def run_read_leg(lib, dist, args, peaks, windows):
     }
 
 
+def run_dist_reorder_leg(lib, dist, args, peaks, windows):
+    """Config 3 read-back: ONE args.particles-particle frame whose rows are partitioned over the ranks (rank r holds
+    file partition r, as after pgsd_read_chunk(all=true)), put into particle-id order across the GPUs by
+    pgsd_b200_reorder_distributed: records go straight into the owner's HBM over NVLink, owners finish locally."""
+    from pgsd_sph_b200 import _lib
+    from pgsd_sph_b200.devmem import DeviceArray
+    n_total = args.particles
+    all_rows, start = rank_rows(n_total, dist.world, dist.rank)
+    rows = all_rows[dist.rank]
+    cols = make_soa(n_total, start, rows, 4242)
+    ids = cols[9]
+    cols[8] = (ids ^ np.uint32(0x9e3779b9)).astype(np.uint32)      # typeid column carries a function of the id: checkable
+    pos = np.ascontiguousarray(np.stack(cols[0:3], axis=1))
+    vel = np.ascontiguousarray(np.stack(cols[3:6], axis=1))
+    host_fields = [pos, vel, cols[8], cols[6], cols[7]]
+    first, cap = C.c_uint64(), C.c_uint64()
+    _lib.check(lib.pgsd_b200_reorder_distributed_plan(n_total, dist.world, dist.rank, C.byref(first), C.byref(cap)), "plan")
+    cap = int(cap.value)
+    d_in = [DeviceArray.from_numpy(a) for a in host_fields]
+    d_out = [DeviceArray((cap,) + a.shape[1:], a.dtype) for a in host_fields]
+    d_ids = DeviceArray.from_numpy(ids)
+    d_sorted = DeviceArray((cap,), np.uint32)
+    fields = (_lib.Field * 5)(*[_lib.Field(i.ptr, o.ptr, a.dtype.itemsize * (a.shape[1] if a.ndim > 1 else 1))
+                                for i, o, a in zip(d_in, d_out, host_fields)])
+    n_out, id_first = C.c_uint64(), C.c_uint64()
+
+    def step():
+        rc = lib.pgsd_b200_reorder_distributed(rows, d_ids.ptr, cap, C.byref(n_out), C.byref(id_first), d_sorted.ptr, 5, fields, None)
+        if rc != 0:
+            raise RuntimeError(f"reorder_distributed rc={rc}: {lib.pgsd_b200_last_error().decode()}")
+
+    for _ in range(args.warmup):
+        step()
+    lib.pgsd_b200_reset_stats()
+    tm = Timer(lib)
+    dist.barrier()
+    lib.pgsd_b200_synchronize()
+    w0 = time.perf_counter()
+    tm.start()
+    for _ in range(args.steps):
+        step()
+    dev_ms = tm.stop()
+    wall = time.perf_counter() - w0
+    dist.barrier()
+    windows.append((w0, time.perf_counter()))
+    st = get_stats(lib)
+    dev_ms = dist.max(dev_ms)
+    wall = dist.max(wall)
+    k, f0 = int(n_out.value), int(id_first.value)
+    got = d_sorted.to_numpy()[:k]
+    assert np.array_equal(got, np.arange(f0, f0 + k, dtype=np.uint32)), "owned ids are not consecutive"
+    assert np.array_equal(d_out[2].to_numpy()[:k], got ^ np.uint32(0x9e3779b9)), "payload does not follow its id"
+    assert int(dist.sum(float(k))) == n_total
+    for a in d_in + d_out + [d_ids, d_sorted]:
+        a.free()
+    value = n_total * args.steps / (dev_ms * 1e-3) / 1e6
+    return {
+        "metric": "distributed_id_reorder_Mparticles_per_s", "value": value, "unit": "Mparticles/s",
+        "ms_per_step": dev_ms / args.steps, "wall_ms_per_step": 1e3 * wall / args.steps, "scaling": "strong",
+        "config": {"workload": f"config 3 read-back: one {n_total}-particle frame, rows partitioned over {dist.world} rank(s), "
+                               "40 B/particle, ids dense and unsorted; fields resident in HBM on both sides",
+                   "comm": lib.pgsd_b200_comm_kind().decode(),
+                   "timed": "whole collective call (5 host all-gathers of sizes / IPC handles / bucket counts / flags, "
+                            "histogram, scatter over NVLink, placement), CUDA events on the stream, max over ranks"},
+        "rows_owned_rank0": k, "gpu_launches": int(dist.sum(float(st.kernel_launches))),
+        "collectives_per_step": st.collectives // max(args.steps, 1),
+    }
+
+
 def run_write_leg(lib, dist, args, peaks, windows):
     from pgsd_sph_b200 import _lib, fl, synth
     from pgsd_sph_b200.devmem import DeviceArray, PinnedArray
@@ -698,6 +767,7 @@ def main():
     if dist.world > 1:
         from pgsd_sph_b200 import comm
         comm.init_nccl(dist.rank, dist.world, dist.bcast_bytes, dist.local)
+    dr = run_dist_reorder_leg(lib, dist, args, peaks, windows)
     wr = run_write_leg(lib, dist, args, peaks, windows)
     bw = None if args.quick else run_benchmark_write_leg(lib, dist, args)
     sampler.stop()
@@ -709,8 +779,8 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": wr["ms_per_step"], "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(common_cfg, comm=lib.pgsd_b200_comm_kind().decode(), parallelism=f"rows/{dist.world}"),
-            "e2e": wr["e2e"], "roofline": wr["roofline"], "gpu_launches": wr["gpu_launches"] + rd["gpu_launches"],
-            "split": wr["split"], "read_reorder": rd, "benchmark_write": bw, "clocks": sampler.summary(windows),
+            "e2e": wr["e2e"], "roofline": wr["roofline"], "gpu_launches": wr["gpu_launches"] + rd["gpu_launches"] + dr["gpu_launches"],
+            "split": wr["split"], "read_reorder": rd, "distributed_reorder": dr, "benchmark_write": bw, "clocks": sampler.summary(windows),
             "vs_baseline_note": "BASELINE.md's only published number (0.175 GB/s benchmark-write, f64 keys, NVMe) is "
                                 "for another workload and storage; not used",
         }

@@ -168,6 +168,10 @@ int pgsd_b200_reorder_host(uint64_t n, const uint32_t* keys_host, uint32_t* keys
    Returns 0, a negative pgsd error, or 1 on EVERY rank when the ids are not unique or not all below
    ceil(N / C) * C (dense ids 0..N-1 qualify): nothing was written, gather the frame to one GPU and use
    pgsd_b200_reorder_device.  row_bytes must be multiples of 4; keys 16-byte aligned. */
+/* Host-only: which ids rank `rank` of `nranks` will own for a frame of n_global rows -- [*id_first,
+   *id_first + *max_rows) -- so that callers can size their outputs before the collective call. */
+int pgsd_b200_reorder_distributed_plan(uint64_t n_global, int nranks, int rank, uint64_t* id_first,
+                                       uint64_t* max_rows);
 int pgsd_b200_reorder_distributed(uint64_t n_local, const uint32_t* keys_device, uint64_t out_capacity,
                                   uint64_t* n_out, uint64_t* id_first, uint32_t* keys_sorted_device,
                                   int nfields, const struct pgsd_b200_field* fields_device, void* cuda_stream);

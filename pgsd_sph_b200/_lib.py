@@ -175,6 +175,7 @@ SIGNATURES = {
     "pgsd_b200_sort_ids": (_i, [_u64, _vp, _vp, _vp, _vp]),
     "pgsd_b200_gather": (_i, [_u64, _vp, _i, C.POINTER(Field), _vp]),
     "pgsd_b200_reorder_device": (_i, [_u64, _vp, _vp, _vp, _i, C.POINTER(Field), _vp]),
+    "pgsd_b200_reorder_distributed_plan": (_i, [_u64, _i, _i, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "pgsd_b200_reorder_distributed": (_i, [_u64, _vp, _u64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), _vp, _i,
                                             C.POINTER(Field), _vp]),
     "pgsd_b200_reorder_host": (_i, [_u64, _vp, _vp, _vp, _i, C.POINTER(Field)]),

@@ -281,6 +281,16 @@ int pgsd_b200_reorder_host(uint64_t n, const uint32_t* keys_host, uint32_t* keys
     return dev_reorder_host(n, keys_host, keys_sorted_host, perm_host, nfields, f.data());
     }
 
+int pgsd_b200_reorder_distributed_plan(uint64_t n_global, int nranks, int rank, uint64_t* id_first, uint64_t* max_rows)
+    {
+    DistPlan pl;
+    if (rank < 0 || rank >= nranks || id_first == nullptr || max_rows == nullptr || dist_plan(n_global, nranks, &pl) != 0)
+        return PGSD_ERROR_INVALID_ARGUMENT;
+    *id_first = (uint64_t)rank * pl.nbr * pl.cap;
+    *max_rows = (uint64_t)pl.nbr * pl.cap;
+    return PGSD_SUCCESS;
+    }
+
 int pgsd_b200_reorder_distributed(uint64_t n_local, const uint32_t* keys_device, uint64_t out_capacity,
                                   uint64_t* n_out, uint64_t* id_first, uint32_t* keys_sorted_device,
                                   int nfields, const struct pgsd_b200_field* fields_device, void* cuda_stream)

@@ -1,6 +1,7 @@
 // comm.cpp -- host-side transports of the rank communicator (single / host callback / shm).
 // The NCCL transport lives in device.cu next to the K2 scan kernel.
 #include "comm.h"
+#include "device.h"
 
 #include <cerrno>
 #include <cstdio>
@@ -248,5 +249,26 @@ Comm* make_shm_comm(int rank, int nprocs, const char* name, std::string& err)
         }
     pthread_barrier_wait(&c->seg->barrier);
     return c;
+    }
+
+// geometry of the distributed reorder (device.h); host-only so that CPU tests and callers can use it
+int dist_plan(uint64_t n_global, int nranks, DistPlan* out)
+    {
+    if (n_global == 0 || n_global >= 0xffffffffull || nranks < 1 || nranks > 8)
+        return -2;
+    int tg = 0;
+    while (tg < 32 && ((n_global - 1) >> tg) != 0)
+        tg++;
+    int L = 10;                 // SLOT_MIN_BITS
+    while (tg - L > 15)         // SLOT_MAX_BUCKET_BITS
+        L++;
+    if (L > 12)                 // SLOT_MAX_BITS
+        return -2;
+    out->L = L;
+    out->cap = 1u << L;
+    out->nbp = 1u << (tg > L ? tg - L : 0);
+    out->nb_used = (uint32_t)((n_global + out->cap - 1) / out->cap);
+    out->nbr = (out->nb_used + (uint32_t)nranks - 1) / (uint32_t)nranks;
+    return 0;
     }
 } // namespace pgsdb

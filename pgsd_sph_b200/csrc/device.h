@@ -96,6 +96,14 @@ int dev_reorder(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, uint32_
                 const ReorderField* fields, void* stream);
 int dev_reorder_host(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, uint32_t* perm,
                      int nfields, const ReorderField* fields);
+// Geometry of the distributed reorder, a pure function of (rows in total, ranks): 2^L ids per bucket, nbp =
+// histogram size (power of two), nb_used = ceil(N / 2^L) buckets hold ids, every rank owns nbr consecutive ones.
+struct DistPlan
+    {
+    int L;
+    uint32_t cap, nbp, nb_used, nbr;
+    };
+int dist_plan(uint64_t n_global, int nranks, DistPlan* out); // 0, or -2 when the frame does not fit the geometry
 // one frame partitioned over the ranks (kernels_slot.cu); 1 = ids not unique / not dense, nothing written
 int dev_reorder_distributed(uint64_t n_local, const uint32_t* keys, uint64_t out_capacity, uint64_t* n_out,
                             uint64_t* id_first, uint32_t* keys_sorted, int nfields, const ReorderField* fields,

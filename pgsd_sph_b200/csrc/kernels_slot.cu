@@ -1024,23 +1024,24 @@ int dev_reorder_distributed(uint64_t n_local, const uint32_t* keys, uint64_t out
         set_last_error("reorder_distributed: fewer than 2^32 - 1 rows in total");
         return -2;
         }
-    int tg = 0;
-    while (tg < 32 && ((N - 1) >> tg) != 0)
-        tg++;
-    int L = SLOT_MIN_BITS;
-    while (tg - L > SLOT_MAX_BUCKET_BITS)
-        L++;
-    const size_t place_smem = slot_place_smem(L, a.row_words);
-    if (L > SLOT_MAX_BITS || place_smem > 220 * 1024)
+    DistPlan pl;
+    if (dist_plan(N, G, &pl) != 0)
         {
         set_last_error("reorder_distributed: frame too large for the slot geometry");
         return -2;
         }
-    const uint32_t cap = 1u << L;
-    const uint32_t nbp = 1u << (tg > L ? tg - L : 0); // histogram size (power of two)
+    const int L = pl.L;
+    const size_t place_smem = slot_place_smem(L, a.row_words);
+    if (place_smem > 220 * 1024)
+        {
+        set_last_error("reorder_distributed: rows too wide for the slot geometry");
+        return -2;
+        }
+    const uint32_t cap = pl.cap;
+    const uint32_t nbp = pl.nbp; // histogram size (power of two)
     const uint32_t bmask = nbp - 1u;
-    const uint32_t nb_used = (uint32_t)((N + cap - 1) / cap);
-    const uint32_t nbr = (nb_used + (uint32_t)G - 1) / (uint32_t)G; // buckets per owner
+    const uint32_t nb_used = pl.nb_used;
+    const uint32_t nbr = pl.nbr; // buckets per owner
     const uint64_t key_limit = (uint64_t)nb_used * cap;             // <= 2^27
     const uint32_t my_b0 = (uint32_t)me * nbr < nb_used ? (uint32_t)me * nbr : nb_used;
     const uint32_t my_b1 = my_b0 + nbr < nb_used ? my_b0 + nbr : nb_used;

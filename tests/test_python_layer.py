@@ -174,3 +174,28 @@ def test_vtu_point_arrays_and_file(golden, tmp_path):
     first = int.from_bytes(tail[:8], 'little')
     assert first == n * 3 * 8
     assert np.frombuffer(tail[8:8 + first], dtype=np.float64).reshape(n, 3)[:, 1].tobytes() == y.tobytes()
+
+
+def test_reorder_distributed_plan_tiles_the_id_space():
+    """Host-side ownership of pgsd_b200_reorder_distributed (include/pgsd_b200.h): the ranks' id ranges are
+    consecutive, equally sized, cover every id of a dense frame, and rank order is id order."""
+    import ctypes as C
+    from pgsd_sph_b200 import _lib
+    lib = _lib.load()
+    for n in (1, 2, 1023, 1024, 1025, 5000, 300001, 1 << 20, (1 << 24) + 5, 64 << 20, 100 << 20):
+        for ranks in (1, 2, 3, 4, 8):
+            spans = []
+            for r in range(ranks):
+                first, rows = C.c_uint64(), C.c_uint64()
+                assert lib.pgsd_b200_reorder_distributed_plan(n, ranks, r, C.byref(first), C.byref(rows)) == 0
+                spans.append((first.value, rows.value))
+            size = spans[0][1]
+            cap = 1024 if n <= (32 << 20) else (2048 if n <= (64 << 20) else 4096)
+            assert size % cap == 0 and all(s == (r * size, size) for r, s in enumerate(spans))
+            assert ranks * size >= n                      # every id 0..n-1 has an owner
+            assert (ranks * size - n) < ranks * cap       # balanced to one bucket per rank
+    bad = C.c_uint64()
+    assert lib.pgsd_b200_reorder_distributed_plan(0, 2, 0, C.byref(bad), C.byref(bad)) < 0
+    assert lib.pgsd_b200_reorder_distributed_plan(1 << 32, 2, 0, C.byref(bad), C.byref(bad)) < 0
+    assert lib.pgsd_b200_reorder_distributed_plan(1000, 9, 0, C.byref(bad), C.byref(bad)) < 0
+    assert lib.pgsd_b200_reorder_distributed_plan(1000, 2, 2, C.byref(bad), C.byref(bad)) < 0
