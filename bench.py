@@ -703,6 +703,8 @@ def main():
     ap.add_argument("--read-particles", type=int, default=READ_PARTICLES)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="skip the 14 GB benchmark-write leg (contract tests)")
+    ap.add_argument("--only-distributed", action="store_true",
+                    help="development: run only the distributed-reorder leg and print its object")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     ncores = os.cpu_count() or 1
@@ -763,6 +765,21 @@ def main():
     if dist.rank == 0:
         sampler.start()
     windows = []
+    if args.only_distributed:
+        if dist.world > 1:
+            from pgsd_sph_b200 import comm
+            comm.init_nccl(dist.rank, dist.world, dist.bcast_bytes, dist.local)
+        dr = run_dist_reorder_leg(lib, dist, args, peaks, windows)
+        sampler.stop()
+        if dist.rank == 0:
+            dr["n_gpus"] = dist.world
+            dr["clocks"] = sampler.summary(windows)
+            print(json.dumps(dr), flush=True)
+        if dist.world > 1:
+            lib.pgsd_b200_comm_finalize()
+        dist.close()
+        lib.pgsd_b200_shutdown()
+        return 0
     rd = run_read_leg(lib, dist, args, peaks, windows)   # communicator: "single" (frames are independent)
     if dist.world > 1:
         from pgsd_sph_b200 import comm

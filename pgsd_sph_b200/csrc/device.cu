@@ -1012,7 +1012,7 @@ class NcclComm : public Comm
     public:
     enum
         {
-        MAX_WORDS = 4096 // u64 values per rank per collective
+        MAX_WORDS = 32768 // u64 values per rank per collective (the bucket counts of a distributed reorder: <= 16385)
         };
     ncclComm_t comm = nullptr;
     cudaStream_t st = nullptr;

@@ -918,8 +918,8 @@ int dev_reorder_slot(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, ui
 // 40-byte rows, then local sort + gather".  Here the all-to-all is not a separate step: k6_slot_scatter writes
 // every record straight into the owner's interleaved copy -- its own memory or a CUDA IPC mapping of the peer's,
 // i.e. plain stores over NVLink -- and each owner then runs the unchanged k6_slot_place on its buckets.
-//   1 all-gather  n_local, output capacity, size of the shared copy   (-> geometry, same on every rank)
-//   2 all-gather  IPC handle of the shared copy                       (mappings are cached between calls)
+//   1 all-gather  n_local, output capacity, size + IPC handle of the shared copy (-> geometry, same on every rank;
+//   2             mappings are cached between calls; a second exchange only when the copy has to grow)
 //   3 k6_slot_hist on the local keys; all-gather of the bucket counts (+ the range flag): every rank now knows
 //     where its records start inside every bucket (sum of the counts of lower ranks: cursors need no remote
 //     atomics), how many rows every rank will own, and whether a bucket overflows -- identical decisions
@@ -1006,14 +1006,32 @@ int dev_reorder_distributed(uint64_t n_local, const uint32_t* keys, uint64_t out
     a.nranks = G;
     a.bulk = aligned ? 1 : 0;
 
-    // (1) sizes
-    uint64_t mine[3] = { n_local, out_capacity, (uint64_t)g_dist_copy_bytes };
-    std::vector<uint64_t> all((size_t)G * 3);
-    if (c->allgather(mine, all.data(), 3) != 0)
+    // (1) sizes, and the IPC handle of the shared copy each rank has right now (valid unless somebody must grow)
+    auto export_copy = [&](uint64_t* w9)
+        {
+        memset(w9, 0, 9 * sizeof(uint64_t));
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+        w9[8] = g_dist_copy ? 1 : 0;
+        if (g_dist_copy && G > 1)
+            {
+            cudaIpcMemHandle_t h;
+            if (cudaIpcGetMemHandle(&h, g_dist_copy) != cudaSuccess)
+                {
+                cudaGetLastError();
+                w9[8] = 0;
+                }
+            else
+                memcpy(w9, &h, 64);
+            }
+        };
+    uint64_t mine[12] = { n_local, out_capacity, (uint64_t)g_dist_copy_bytes };
+    export_copy(mine + 3);
+    std::vector<uint64_t> all((size_t)G * 12);
+    if (c->allgather(mine, all.data(), 12) != 0)
         return -1;
     uint64_t N = 0;
     for (int p = 0; p < G; p++)
-        N += all[(size_t)p * 3];
+        N += all[(size_t)p * 12];
     *n_out = 0;
     if (id_first)
         *id_first = 0;
@@ -1058,8 +1076,9 @@ int dev_reorder_distributed(uint64_t n_local, const uint32_t* keys, uint64_t out
     const size_t copy_need = up256((size_t)nbr * nlines * 128) + 256;
     bool grow = false;
     for (int p = 0; p < G; p++)
-        if (all[(size_t)p * 3 + 2] < copy_need)
+        if (all[(size_t)p * 12 + 2] < copy_need)
             grow = true;
+    std::vector<uint64_t> hall((size_t)G * 9);
     if (grow)
         {
         dist_close_peers();
@@ -1074,25 +1093,14 @@ int dev_reorder_distributed(uint64_t n_local, const uint32_t* keys, uint64_t out
             g_dist_copy_bytes = copy_need;
         else
             cudaGetLastError();
+        uint64_t hsend[9];
+        export_copy(hsend);
+        if (c->allgather(hsend, hall.data(), 9) != 0)
+            return -1;
         }
-    uint64_t hsend[9];
-    memset(hsend, 0, sizeof(hsend));
-    cudaIpcMemHandle_t myh;
-    memset(&myh, 0, sizeof(myh));
-    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-    hsend[8] = g_dist_copy ? 1 : 0;
-    if (g_dist_copy && G > 1)
-        {
-        if (cudaIpcGetMemHandle(&myh, g_dist_copy) != cudaSuccess)
-            {
-            cudaGetLastError();
-            hsend[8] = 0;
-            }
-        memcpy(hsend, &myh, 64);
-        }
-    std::vector<uint64_t> hall((size_t)G * 9);
-    if (c->allgather(hsend, hall.data(), 9) != 0)
-        return -1;
+    else
+        for (int p = 0; p < G; p++)
+            memcpy(&hall[(size_t)p * 9], &all[(size_t)p * 12 + 3], 9 * sizeof(uint64_t));
     for (int p = 0; p < G; p++)
         if (hall[(size_t)p * 9 + 8] == 0)
             {
@@ -1242,7 +1250,7 @@ int dev_reorder_distributed(uint64_t n_local, const uint32_t* keys, uint64_t out
         return 1; // more ids than slots in a bucket: duplicates
     bool fits = true;
     for (int p = 0; p < G; p++)
-        if (owned[p] > all[(size_t)p * 3 + 1])
+        if (owned[p] > all[(size_t)p * 12 + 1])
             fits = false;
     if (!fits)
         {
