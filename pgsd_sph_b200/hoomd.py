@@ -275,6 +275,57 @@ def reorder_by_id(ids, arrays, device=False):
     return sorted_ids, outs
 
 
+def reorder_by_id_distributed(ids, arrays):
+    """Particle-ID order for ONE frame whose rows are partitioned over the ranks (one process per GPU; every rank
+    calls this with the partition it holds, e.g. what ``read_chunk(..., r_all=True, device=True)`` returned).
+
+    ``ids``: uint32 device array of this rank's keys; ``arrays``: dict of device arrays with as many rows.
+    Returns ``(first_id, sorted ids, dict)``: this rank's share of the ID-ordered frame -- the rows whose ids
+    lie in ``[first_id, first_id + S)`` (``S`` from ``pgsd_b200_reorder_distributed_plan``), as DeviceArrays
+    trimmed to the rows actually owned.  Concatenated over the ranks in rank order this equals
+    ``o = numpy.argsort(all_ids, kind='stable'); {k: all_v[o]}`` bit for bit.  Raises ``ValueError`` (on every
+    rank) when the ids are not unique or not dense enough; gather the frame to one GPU and use
+    :py:func:`reorder_by_id` then.  Collective: the records travel GPU to GPU inside the scatter kernel.
+    """
+    import ctypes as C
+    from .devmem import as_device_view
+    lib = _lib.load()
+    names = list(arrays.keys())
+    kptr, kshape, kdt, _, keep = as_device_view(ids)
+    n = int(kshape[0]) if len(kshape) else 1
+    if kdt != numpy.dtype(numpy.uint32):
+        raise ValueError("particle ids must be uint32")
+    rank, nranks = lib.pgsd_b200_comm_rank(), lib.pgsd_b200_comm_size()
+    n_global, row_start = C.c_uint64(), C.c_uint64()
+    _lib.check(lib.pgsd_b200_partition(n, C.byref(n_global), C.byref(row_start)), "pgsd_b200_partition")
+    first, cap = C.c_uint64(), C.c_uint64()
+    if n_global.value == 0:
+        return 0, DeviceArray((0,), numpy.uint32), {k: DeviceArray((0,) + tuple(as_device_view(arrays[k])[1][1:]),
+                                                                    as_device_view(arrays[k])[2]) for k in names}
+    _lib.check(lib.pgsd_b200_reorder_distributed_plan(n_global.value, nranks, rank, C.byref(first), C.byref(cap)),
+               "pgsd_b200_reorder_distributed_plan")
+    cap = int(cap.value)
+    sorted_ids = DeviceArray((cap,), numpy.uint32)
+    outs, fields, keeps = {}, (_lib.Field * max(len(names), 1))(), [keep]
+    for i, k in enumerate(names):
+        ptr, shape, dt, strides, kp = as_device_view(arrays[k])
+        keeps.append(kp)
+        row = dt.itemsize * (int(numpy.prod(shape[1:])) if len(shape) > 1 else 1)
+        outs[k] = DeviceArray((cap,) + tuple(shape[1:]), dt)
+        fields[i] = _lib.Field(ptr, outs[k].ptr, row)
+    n_out, id_first = C.c_uint64(), C.c_uint64()
+    rc = lib.pgsd_b200_reorder_distributed(n, kptr, cap, C.byref(n_out), C.byref(id_first), sorted_ids.ptr, len(names),
+                                           fields, None)
+    if rc == 1:
+        raise ValueError("reorder_by_id_distributed: particle ids are not unique or not dense in [0, N)")
+    _lib.check(rc, "pgsd_b200_reorder_distributed")
+    k_rows = int(n_out.value)
+
+    def trim(a):
+        return DeviceArray((k_rows,) + a.shape[1:], a.dtype, ptr=a.ptr, owner=a)
+    return int(id_first.value), trim(sorted_ids), {k: trim(v) for k, v in outs.items()}
+
+
 class HOOMDTrajectory(object):
     """Read and write hoomd pgsd files (ref: hoomd.py:519-941).
 

@@ -13,6 +13,9 @@ from pgsd_sph_b200 import _lib
 from pgsd_sph_b200.devmem import DeviceArray
 
 
+PYWRAP_N = 200003
+
+
 def cases():
     """name, N, key generator(rng, N) -> uint32 ids of the WHOLE frame; the same on every rank."""
     yield "perm_300k", 300001, lambda rng, n: rng.permutation(n).astype(np.uint32)
@@ -55,6 +58,17 @@ def main():
                  ids=d_sorted.to_numpy()[:k], pos=outs[0].to_numpy()[:k], tag=outs[1].to_numpy()[:k], dens=outs[2].to_numpy()[:k])
         for a in ins + outs + [d_ids, d_sorted]:
             a.free()
+    # the Python-level wrapper (pgsd_sph_b200.hoomd.reorder_by_id_distributed) on one more frame
+    from pgsd_sph_b200 import hoomd
+    n = PYWRAP_N
+    rng = np.random.default_rng(77)
+    ids = rng.permutation(n).astype(np.uint32)
+    pos = rng.standard_normal((n, 3)).astype(np.float32)
+    lo = sum(n // nprocs + (1 if r < n % nprocs else 0) for r in range(rank))
+    cnt = n // nprocs + (1 if rank < n % nprocs else 0)
+    first, sid, out = hoomd.reorder_by_id_distributed(DeviceArray.from_numpy(ids[lo:lo + cnt]),
+                                                      {"pos": DeviceArray.from_numpy(pos[lo:lo + cnt])})
+    np.savez(os.path.join(outdir, f"rank{rank}_pywrap.npz"), id_first=first, ids=sid.to_numpy(), pos=out["pos"].to_numpy())
     lib.pgsd_b200_comm_finalize()
     print(f"rank {rank} ok")
 

@@ -59,3 +59,12 @@ def test_reorder_distributed_equals_stable_argsort(lib, nprocs):
                     assert x["ids"][0] >= x["id_first"]
                     if r + 1 < nprocs:
                         assert x["ids"][-1] < res[r + 1]["id_first"]
+        # Python wrapper
+        rng = np.random.default_rng(77)
+        ids = rng.permutation(W.PYWRAP_N).astype(np.uint32)
+        pos = rng.standard_normal((W.PYWRAP_N, 3)).astype(np.float32)
+        res = [np.load(os.path.join(d, f"rank{r}_pywrap.npz")) for r in range(nprocs)]
+        o = np.argsort(ids, kind='stable')
+        assert np.concatenate([x["ids"] for x in res]).tobytes() == ids[o].tobytes()
+        assert np.concatenate([x["pos"] for x in res]).tobytes() == pos[o].tobytes()
+        assert all(len(x["ids"]) == 0 or x["ids"][0] == x["id_first"] for x in res)
