@@ -18,7 +18,8 @@
 //                    detects duplicates and compacts gaps), and the fields are written back SoA, fully
 //                    coalesced, at the bucket's own output range.
 //
-// Layout of the interleaved copy ("lines", default): 128-byte line j of bucket b is line j * nb + b.  The
+// Layout of the interleaved copy ("lines", default): unit j (256 bytes; PGSD_B200_SLOT_UNIT = log2) of bucket b is
+// unit j * nb + b.  The
 // cursors of all buckets advance at about the same pace, so the lines being filled form ONE compact window
 // that moves through the copy, and the L2 write-backs of completed lines fall into few open DRAM rows.
 // With contiguous buckets ("flat", PGSD_B200_SLOT_LAYOUT=flat: one TMA bulk copy per bucket in
@@ -76,6 +77,7 @@ struct SlotArgs
                   // bucket b lives at line j * nb + b, so that the lines the buckets are currently filling (about the
                   // same j for all of them) form one compact, advancing window instead of nb windows spread over the
                   // whole copy: the L2 write-backs then fall into few open DRAM rows
+    int ushift; // "lines" layout: log2 of the interleaving unit in bytes (7: 128-byte lines)
     // distributed reorder: rank `o` owns the buckets [o * nbr, (o + 1) * nbr); peer[o] is its interleaved copy
     // (own memory, or a CUDA IPC mapping of the owner's memory: the record stores then travel over NVLink)
     uint32_t* peer[8];
@@ -300,7 +302,7 @@ __device__ __forceinline__ void slot_records_out(const uint32_t* __restrict__ ra
                         if (args.nbl)
                             {
                             const uint32_t o = (dd[u] & 4095u) * (RW * 4u) + c2 * 8u;
-                            const uint64_t at = ((uint64_t)((o >> 7) * args.nbl + ((dd[u] >> 12) & 32767u)) << 7) + (o & 127u);
+                            const uint64_t at = ((uint64_t)((o >> args.ushift) * args.nbl + ((dd[u] >> 12) & 32767u)) << args.ushift) + (o & ((1u << args.ushift) - 1u));
                             unsigned char* copy = reinterpret_cast<unsigned char*>(args.nranks > 1 ? args.peer[dd[u] >> 27] : aos);
                             *reinterpret_cast<uint2*>(copy + at) = v[u];
                             }
@@ -339,7 +341,7 @@ __device__ __forceinline__ void slot_records_out(const uint32_t* __restrict__ ra
                         if (args.nbl)
                             {
                             const uint32_t o = (dd[u] & 4095u) * (RW * 4u) + c * 4u;
-                            const uint64_t at = ((uint64_t)((o >> 7) * args.nbl + ((dd[u] >> 12) & 32767u)) << 7) + (o & 127u);
+                            const uint64_t at = ((uint64_t)((o >> args.ushift) * args.nbl + ((dd[u] >> 12) & 32767u)) << args.ushift) + (o & ((1u << args.ushift) - 1u));
                             unsigned char* copy = reinterpret_cast<unsigned char*>(args.nranks > 1 ? args.peer[dd[u] >> 27] : aos);
                             *reinterpret_cast<uint32_t*>(copy + at) = v[u];
                             }
@@ -538,12 +540,13 @@ __global__ void __launch_bounds__(1024) k6_slot_place(const uint32_t* __restrict
     if (args.nbl)
         {
         // "lines" layout: the bucket's 128-byte lines are nb lines apart; 16-byte cp.async pieces
-        const uint32_t pieces = ((cnt * RW * 4u + 127u) >> 7) * 8u;
+        const uint32_t pieces = (cnt * RW * 4u + 15u) >> 4;
         const unsigned char* src = reinterpret_cast<const unsigned char*>(aos);
         const uint32_t sbase = smem_u32(smem_raw);
+        const uint32_t us = (uint32_t)args.ushift - 4u; // 16-byte pieces per unit, log2
         for (uint32_t q = tid; q < pieces; q += nt)
             {
-            const uint64_t at = ((uint64_t)((q >> 3) * args.nbl + blockIdx.x) << 7) + (q & 7u) * 16u;
+            const uint64_t at = ((uint64_t)((q >> us) * args.nbl + blockIdx.x) << args.ushift) + (q & ((1u << us) - 1u)) * 16u;
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + q * 16u), "l"(src + at) : "memory");
             }
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -822,7 +825,16 @@ int dev_reorder_slot(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, ui
     a_place.nbl = a.nbl;
     const size_t tb = up256((size_t)(nb + 1) * 4);
     const size_t cb = up256((size_t)nb * cstride * 4);
-    const size_t copy_bytes = lines ? (size_t)nb * (((size_t)cap * a.row_words * 4 + 127) / 128) * 128 : (size_t)n * a.row_words * 4;
+    int ushift = 8; // 256-byte units: 2 % faster than 128-byte lines, 1 KB and more is slower (profiles/README.md)
+    const char* eu = getenv("PGSD_B200_SLOT_UNIT");
+    if (eu)
+        ushift = atoi(eu);
+    if (ushift < 7 || ushift > 12)
+        ushift = 8;
+    a.ushift = ushift;
+    a_place.ushift = ushift;
+    const size_t unit = (size_t)1 << ushift;
+    const size_t copy_bytes = lines ? (size_t)nb * (((size_t)cap * a.row_words * 4 + unit - 1) / unit) * unit : (size_t)n * a.row_words * 4;
     const size_t need = 256 + 2 * tb + cb + up256(copy_bytes) + 256;
     if (g_slot_ws_bytes < need)
         {
@@ -1004,6 +1016,7 @@ int dev_reorder_distributed(uint64_t n_local, const uint32_t* keys, uint64_t out
     a.nfields = nf;
     a.row_words = off;
     a.nranks = G;
+    a.ushift = 7;
     a.bulk = aligned ? 1 : 0;
 
     // (1) sizes, and the IPC handle of the shared copy each rank has right now (valid unless somebody must grow)

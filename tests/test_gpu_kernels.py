@@ -402,7 +402,7 @@ def test_reorder_slot_path_equals_stable_argsort(cuda, monkeypatch, name, keys, 
             assert launches > max(SLOT_LAUNCHES), launches
 
 
-@pytest.mark.parametrize("bulk", ["1", "0", "flat", "flat-plain"])
+@pytest.mark.parametrize("bulk", ["1", "0", "flat", "flat-plain", "unit128", "unit1024"])
 @pytest.mark.parametrize("tile", ["512", "1024", "2048"])
 @pytest.mark.parametrize("bits", ["10", "11", "12"])
 def test_reorder_slot_path_variants(cuda, monkeypatch, bits, tile, bulk):
@@ -414,6 +414,8 @@ def test_reorder_slot_path_variants(cuda, monkeypatch, bits, tile, bulk):
     if bulk.startswith("flat"):
         monkeypatch.setenv("PGSD_B200_SLOT_LAYOUT", "flat")
     monkeypatch.setenv("PGSD_B200_SLOT_BULK", "0" if bulk in ("0", "flat-plain") else "1")
+    if bulk.startswith("unit"):
+        monkeypatch.setenv("PGSD_B200_SLOT_UNIT", {"unit128": "7", "unit1024": "10"}[bulk])
     rng = np.random.default_rng(int(bits) * 7 + int(tile))
     n = 150001
     keys = (rng.permutation(n) + rng.integers(0, 2)).astype(np.uint32)

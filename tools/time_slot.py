@@ -10,7 +10,7 @@ from pgsd_sph_b200.devmem import DeviceArray
 lib = _lib.load(); _lib.check(lib.pgsd_b200_device_init(0), "init")
 PEAK = 6546.6
 t = C.c_void_p(); lib.pgsd_b200_timer_create(C.byref(t))
-KNOBS = ["PGSD_B200_SLOT_LAYOUT", "PGSD_B200_SLOT_CSTRIDE", "PGSD_B200_SLOT_DEBUG", "PGSD_B200_SLOT", "PGSD_B200_SLOT_BITS", "PGSD_B200_SLOT_TILE", "PGSD_B200_SLOT_BULK"]
+KNOBS = ["PGSD_B200_SLOT_UNIT", "PGSD_B200_SLOT_LAYOUT", "PGSD_B200_SLOT_CSTRIDE", "PGSD_B200_SLOT_DEBUG", "PGSD_B200_SLOT", "PGSD_B200_SLOT_BITS", "PGSD_B200_SLOT_TILE", "PGSD_B200_SLOT_BULK"]
 VARIANTS = [
     ("general path", {"PGSD_B200_SLOT": "0"}),
     ("slot default", {}),
@@ -18,6 +18,11 @@ VARIANTS = [
     ("slot tile 2048", {"PGSD_B200_SLOT_TILE": "2048"}),
     ("slot bits 11", {"PGSD_B200_SLOT_BITS": "11"}),
     ("slot bits 12", {"PGSD_B200_SLOT_BITS": "12"}),
+    ("slot unit 256", {"PGSD_B200_SLOT_UNIT": "8"}),
+    ("slot unit 512", {"PGSD_B200_SLOT_UNIT": "9"}),
+    ("slot unit 1024", {"PGSD_B200_SLOT_UNIT": "10"}),
+    ("slot unit 2048", {"PGSD_B200_SLOT_UNIT": "11"}),
+    ("slot unit 4096", {"PGSD_B200_SLOT_UNIT": "12"}),
     ("slot flat", {"PGSD_B200_SLOT_LAYOUT": "flat"}),
     ("slot flat plain loads", {"PGSD_B200_SLOT_LAYOUT": "flat", "PGSD_B200_SLOT_BULK": "0"}),
     ("slot flat cstride 1", {"PGSD_B200_SLOT_LAYOUT": "flat", "PGSD_B200_SLOT_CSTRIDE": "1"}),
