@@ -47,6 +47,8 @@
 
 #include "comm.h"
 
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <vector>
 
@@ -965,6 +967,30 @@ void dist_release_workspace()
     g_dist_copy_bytes = 0;
     }
 
+// PGSD_B200_DIST_TRACE=1: rank 0 prints the host wall time of every stage of a distributed reorder to stderr
+struct DistTrace
+    {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    std::string line;
+    explicit DistTrace(bool enable) : on(enable), t0(std::chrono::steady_clock::now()) { }
+    void mark(const char* what)
+        {
+        if (!on)
+            return;
+        const auto t1 = std::chrono::steady_clock::now();
+        char buf[96];
+        snprintf(buf, sizeof(buf), " %s %.0f us;", what, std::chrono::duration<double, std::micro>(t1 - t0).count());
+        line += buf;
+        t0 = t1;
+        }
+    ~DistTrace()
+        {
+        if (on)
+            fprintf(stderr, "[pgsd_b200 reorder_distributed]%s\n", line.c_str());
+        }
+    };
+
 int dev_reorder_distributed(uint64_t n_local, const uint32_t* keys, uint64_t out_capacity, uint64_t* n_out, uint64_t* id_first,
                             uint32_t* keys_sorted, int nfields, const ReorderField* fields, void* stream_v)
     {
@@ -973,6 +999,8 @@ int dev_reorder_distributed(uint64_t n_local, const uint32_t* keys, uint64_t out
         return rc;
     Comm* c = comm();
     const int G = c->nprocs, me = c->rank;
+    const char* etr = getenv("PGSD_B200_DIST_TRACE");
+    DistTrace trace(etr && etr[0] == '1' && me == 0);
     if (G > 8)
         {
         set_last_error("reorder_distributed: at most 8 ranks");
@@ -1042,6 +1070,7 @@ int dev_reorder_distributed(uint64_t n_local, const uint32_t* keys, uint64_t out
     std::vector<uint64_t> all((size_t)G * 12);
     if (c->allgather(mine, all.data(), 12) != 0)
         return -1;
+    trace.mark("allgather(sizes+handles)");
     uint64_t N = 0;
     for (int p = 0; p < G; p++)
         N += all[(size_t)p * 12];
@@ -1194,6 +1223,7 @@ int dev_reorder_distributed(uint64_t n_local, const uint32_t* keys, uint64_t out
     uint32_t* start = (uint32_t*)(p8 + 256 + tb + bb);
     uint32_t* cursor = (uint32_t*)(p8 + 256 + 2 * tb + bb);
 
+    trace.mark("peers+workspace");
     // (3) local histogram, counts of all ranks
     const size_t cw = ((size_t)nbp + 1) / 2 + 1; // u64 words: packed counts + status word
     std::vector<uint64_t> csend(cw, 0), call((size_t)G * cw);
@@ -1221,10 +1251,12 @@ int dev_reorder_distributed(uint64_t n_local, const uint32_t* keys, uint64_t out
         else if (g_slot_flag_host[2] != 0)
             status |= 1;
         }
+    trace.mark("hist+D2H");
     memcpy(csend.data(), hcounts.data(), (size_t)nbp * 4);
     csend[cw - 1] = status;
     if (c->allgather(csend.data(), call.data(), cw) != 0)
         return -1;
+    trace.mark("allgather(counts)");
     uint64_t any = 0;
     for (int p = 0; p < G; p++)
         any |= call[(size_t)p * cw + cw - 1];
@@ -1239,25 +1271,24 @@ int dev_reorder_distributed(uint64_t n_local, const uint32_t* keys, uint64_t out
     std::vector<uint32_t> hstart(nbp, 0), hbase((size_t)nbr + 2, 0);
     std::vector<uint64_t> owned(G, 0);
     bool overflow = false;
-    for (uint32_t b = 0; b < nbp; b++)
+    std::vector<uint32_t> htot(nbp, 0);
+    for (int p = 0; p < G; p++) // rank by rank over contiguous rows of the gathered table
         {
-        uint32_t tot = 0;
-        for (int p = 0; p < G; p++)
-            {
-            const uint32_t cpb = reinterpret_cast<const uint32_t*>(&call[(size_t)p * cw])[b];
-            if (p == me)
-                hstart[b] = tot;
-            tot += cpb;
-            }
-        if (tot > cap)
+        const uint32_t* cp = reinterpret_cast<const uint32_t*>(&call[(size_t)p * cw]);
+        if (p == me)
+            memcpy(hstart.data(), htot.data(), (size_t)nbp * 4);
+        for (uint32_t b = 0; b < nbp; b++)
+            htot[b] += cp[b];
+        }
+    for (uint32_t b = 0; b < nbp; b++)
+        if (htot[b] > cap)
             overflow = true;
+    for (uint32_t b = 0; b < nb_used; b++)
+        {
         const uint32_t o = b / nbr;
-        if (b < nb_used && o < (uint32_t)G)
-            {
-            owned[o] += tot;
-            if (o == (uint32_t)me)
-                hbase[b - my_b0 + 1] = tot;
-            }
+        owned[o] += htot[b];
+        if (o == (uint32_t)me)
+            hbase[b - my_b0 + 1] = htot[b];
         }
     if (overflow)
         return 1; // more ids than slots in a bucket: duplicates
@@ -1279,6 +1310,7 @@ int dev_reorder_distributed(uint64_t n_local, const uint32_t* keys, uint64_t out
     k6_slot_spread<<<(nbp + 255) / 256, 256, 0, st>>>(start, nbp, cursor, cstride);
     dev_stats().kernel_launches++;
 
+    trace.mark("tables+H2D");
     // (4) records to their owners
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess && n_local > 0)
@@ -1298,9 +1330,11 @@ int dev_reorder_distributed(uint64_t n_local, const uint32_t* keys, uint64_t out
         }
     else if (g_slot_flag_host[1] == 3)
         st4 = 4;
+    trace.mark("scatter+sync");
     std::vector<uint64_t> sall(G);
     if (c->allgather(&st4, sall.data(), 1) != 0) // also the barrier: every record has reached its owner
         return -1;
+    trace.mark("allgather(barrier)");
     for (int p = 0; p < G; p++)
         if (sall[p] != 0)
             {
@@ -1327,8 +1361,10 @@ int dev_reorder_distributed(uint64_t n_local, const uint32_t* keys, uint64_t out
         else if (g_slot_flag_host[1] != 0)
             st5 = 1; // two records of a bucket share a slot
         }
+    trace.mark("place+sync");
     if (c->allgather(&st5, sall.data(), 1) != 0)
         return -1;
+    trace.mark("allgather(flags)");
     any = 0;
     for (int p = 0; p < G; p++)
         any |= sall[p];

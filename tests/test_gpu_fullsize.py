@@ -86,3 +86,35 @@ def test_64M_frame_reads_back_and_reorders(big_file):
         # a permutation preserves every column's multiset: checksum of checksums
         assert int(fr.particles.typeid.astype(np.uint64).sum()) == int(cols[8].astype(np.uint64).sum())
         assert fr.particles.pressure.view(np.uint32).astype(np.uint64).sum() == cols[7].view(np.uint32).astype(np.uint64).sum()
+
+
+def test_100M_reorder_widest_slot_geometry(lib):
+    """More than 64 Mi particles: the slot path needs 4096-id buckets (160 KB of shared memory per bucket, one
+    CTA per SM) and 25600 of them.  Size-independent checks: sorted ids are 0..N-1 and a payload that is a
+    function of its id lands at row id."""
+    from pgsd_sph_b200 import _lib
+    assert lib.pgsd_b200_cuda_available() == 1, "no CUDA device: the device path has no CPU fallback"
+    n = 100 * 1024 * 1024
+    rng = np.random.Generator(np.random.PCG64(7))
+    ids = rng.permutation(n).astype(np.uint32)
+    tag = ids ^ np.uint32(0x5bd1e995)
+    pos = np.empty((n, 3), dtype=np.float32)
+    pos[:, 0] = ids
+    pos[:, 1] = ids * np.float32(0.25)
+    pos[:, 2] = -pos[:, 0]
+    d_ids, d_tag, d_pos = DeviceArray.from_numpy(ids), DeviceArray.from_numpy(tag), DeviceArray.from_numpy(pos)
+    o_ids, o_tag, o_pos = DeviceArray((n,), np.uint32), DeviceArray((n,), np.uint32), DeviceArray((n, 3), np.float32)
+    fields = (_lib.Field * 2)(_lib.Field(d_tag.ptr, o_tag.ptr, 4), _lib.Field(d_pos.ptr, o_pos.ptr, 12))
+    lib.pgsd_b200_reset_stats()
+    _lib.check(lib.pgsd_b200_reorder_device(n, d_ids.ptr, o_ids.ptr, None, 2, fields, None), "reorder_device")
+    _lib.check(lib.pgsd_b200_synchronize(), "sync")
+    st = _lib.Stats()
+    lib.pgsd_b200_get_stats(st)
+    assert st.kernel_launches == 4, st.kernel_launches          # histogram, scan, scatter, place: the slot path
+    ar = np.arange(n, dtype=np.uint32)
+    assert np.array_equal(o_ids.to_numpy(), ar)
+    assert np.array_equal(o_tag.to_numpy(), ar ^ np.uint32(0x5bd1e995))
+    got = o_pos.to_numpy()
+    assert np.array_equal(got[:, 0], ar.astype(np.float32)) and np.array_equal(got[:, 2], -ar.astype(np.float32))
+    for a in (d_ids, d_tag, d_pos, o_ids, o_tag, o_pos):
+        a.free()

@@ -453,6 +453,32 @@ def test_reorder_slot_path_row_widths(cuda, monkeypatch, widths, layout):
             assert g.tobytes() == f[o].tobytes()
 
 
+@pytest.mark.parametrize("seed", range(24))
+def test_reorder_slot_path_random_geometry(cuda, monkeypatch, seed):
+    """Seeded random cases: n, id range (10..27 bits, so every bucket count from 1 to 32768 and every slot width),
+    density of the ids in that range, an id offset, record shape and whether the permutation is wanted.
+    Always == numpy stable argsort + gather, bit for bit."""
+    monkeypatch.setenv("PGSD_B200_BUCKET_MIN_ROWS", "0")
+    rng = np.random.default_rng(9000 + seed)
+    bits = int(rng.integers(10, 28))
+    n = int(min(rng.integers(1, 400000), 1 << bits))
+    keys = rng.choice(1 << bits, size=n, replace=False).astype(np.uint32)
+    if rng.random() < 0.3:
+        keys = (keys + np.uint32(rng.integers(1, 1 << 30))).astype(np.uint32)       # ids with an offset
+    if rng.random() < 0.2 and n > 10:
+        keys[int(rng.integers(0, n))] = keys[int(rng.integers(0, n))]               # maybe one duplicate: general path
+    widths = [int(w) for w in rng.integers(1, 6, size=int(rng.integers(1, 6)))]
+    fields = [rng.integers(0, 2 ** 32, size=(n, w), dtype=np.uint64).astype(np.uint32) for w in widths]
+    want_perm = bool(rng.integers(0, 2))
+    o = np.argsort(keys, kind='stable')
+    s, p, outs = _reorder_device_full(cuda, keys, fields, want_perm)
+    assert (s == keys[o]).all()
+    if want_perm:
+        assert (p == o.astype(np.uint32)).all()
+    for f, g in zip(fields, outs):
+        assert g.tobytes() == f[o].tobytes()
+
+
 def test_reorder_slot_path_unaligned_inputs(cuda, monkeypatch):
     """Field arrays that start 4 bytes off a 16-byte boundary are staged with plain loads."""
     monkeypatch.setenv("PGSD_B200_BUCKET_MIN_ROWS", "0")
