@@ -265,10 +265,13 @@ __global__ void __launch_bounds__(1024) k6_slot_scan(const uint32_t* __restrict_
     }
 
 // records out: a group of lanes writes one record (consecutive words), G records per warp store
+// order != NULL: the loop runs over tile positions j sorted by destination and row = order[j], so that the records
+// of one warp store are neighbours at their destination (partition by owner: long contiguous runs).
 template <int NT>
 __device__ __forceinline__ void slot_records_out(const uint32_t* __restrict__ raw, const uint32_t* __restrict__ sdst,
                                                  const uint32_t* __restrict__ col, uint64_t tile0, uint32_t tile_n,
-                                                 uint32_t RW, uint32_t* __restrict__ aos, const SlotArgs& args, int lane, int w)
+                                                 uint32_t RW, uint32_t* __restrict__ aos, const SlotArgs& args, int lane, int w,
+                                                 const uint16_t* __restrict__ order = nullptr)
     {
     constexpr uint32_t NW = NT / 32;
     constexpr int U = 4;
@@ -289,9 +292,10 @@ __device__ __forceinline__ void slot_records_out(const uint32_t* __restrict__ ra
 #pragma unroll
                 for (int u = 0; u < U; u++)
                     {
-                    const uint32_t r = r0 + (uint32_t)u * step;
-                    if (r < tile_n)
+                    const uint32_t j = r0 + (uint32_t)u * step;
+                    if (j < tile_n)
                         {
+                        const uint32_t r = order ? order[j] : j;
                         dd[u] = sdst[r];
                         v[u].x = Wa ? raw[fa + r * Wa] : (uint32_t)(tile0 + r);
                         v[u].y = Wb ? raw[fb + r * Wb] : (uint32_t)(tile0 + r);
@@ -308,6 +312,8 @@ __device__ __forceinline__ void slot_records_out(const uint32_t* __restrict__ ra
                             unsigned char* copy = reinterpret_cast<unsigned char*>(args.nranks > 1 ? args.peer[dd[u] >> 27] : aos);
                             *reinterpret_cast<uint2*>(copy + at) = v[u];
                             }
+                        else if (args.nranks > 1) // record index in the owner's inbox
+                            reinterpret_cast<uint2*>(args.peer[dd[u] >> 27])[(uint64_t)(dd[u] & 0x7ffffffu) * R2 + c2] = v[u];
                         else
                             aos2[(uint64_t)dd[u] * R2 + c2] = v[u];
                         }
@@ -329,9 +335,10 @@ __device__ __forceinline__ void slot_records_out(const uint32_t* __restrict__ ra
 #pragma unroll
                 for (int u = 0; u < U; u++)
                     {
-                    const uint32_t r = r0 + (uint32_t)u * step;
-                    if (r < tile_n)
+                    const uint32_t j = r0 + (uint32_t)u * step;
+                    if (j < tile_n)
                         {
+                        const uint32_t r = order ? order[j] : j;
                         dd[u] = sdst[r];
                         v[u] = W ? raw[fb + r * W] : (uint32_t)(tile0 + r);
                         }
@@ -347,6 +354,8 @@ __device__ __forceinline__ void slot_records_out(const uint32_t* __restrict__ ra
                             unsigned char* copy = reinterpret_cast<unsigned char*>(args.nranks > 1 ? args.peer[dd[u] >> 27] : aos);
                             *reinterpret_cast<uint32_t*>(copy + at) = v[u];
                             }
+                        else if (args.nranks > 1)
+                            args.peer[dd[u] >> 27][(uint64_t)(dd[u] & 0x7ffffffu) * RW + c] = v[u];
                         else
                             aos[(uint64_t)dd[u] * RW + c] = v[u];
                         }
@@ -500,6 +509,208 @@ __global__ void __launch_bounds__(NT) k6_slot_scatter(uint64_t n, uint32_t tile_
         }
     // (3) records out
     slot_records_out<NT>(raw, sdst, col, tile0, tile_n, RW, aos, args, lane, w);
+    }
+
+// ---- distributed reorder, step 1: partition by OWNER ------------------------------------------------------------
+// Same staging as k6_slot_scatter, but a row only needs to reach the rank that owns its id range (<= 8
+// destinations).  The rows of a tile are counted per owner in shared memory, one atomic per (tile, owner) reserves
+// a run in the owner's inbox, and the records leave sorted by owner: every tile writes a few contiguous runs of
+// about T / ranks records (5 KB for the SPH row) -- into its own HBM or, through the IPC mapping, over NVLink.
+template <int T, int NT>
+__global__ void __launch_bounds__(NT) k6_part_scatter(uint64_t n, int L, uint32_t bmask, uint32_t* __restrict__ owner_cursor,
+                                                     uint32_t* __restrict__ flag, const __grid_constant__ SlotArgs args)
+    {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long bar_mem;
+    __shared__ uint32_t col[SLOT_MAX_ROW_WORDS];
+    __shared__ uint32_t scnt[8], sofs[9], sbase[8];
+    uint32_t* raw = reinterpret_cast<uint32_t*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const uint64_t tile0 = (uint64_t)blockIdx.x * T;
+    const uint32_t tile_n = (uint32_t)((n - tile0) < (uint64_t)T ? (n - tile0) : T);
+    const uint32_t RW = args.row_words;
+    constexpr int PER = T / NT;
+
+    uint32_t key[PER];
+#pragma unroll
+    for (int k = 0; k < PER; k++)
+        {
+        const uint32_t r = (uint32_t)tid + (uint32_t)k * NT;
+        key[k] = r < tile_n ? __ldg(args.f[0].in + tile0 + r) : 0u;
+        }
+    uint32_t fbase = 0, tx_bytes = 0;
+    for (int fi = 0; fi < args.nfields; fi++)
+        {
+        const uint32_t W = args.f[fi].words;
+        const bool real = args.f[fi].in != nullptr;
+        if (tid < (int)W)
+            col[args.f[fi].off + tid] = real ? (((fbase + (uint32_t)tid) << 8) | W) : 0u;
+        if (real)
+            {
+            fbase += (uint32_t)T * W + SLOT_SKEW;
+            if (fi > 0)
+                tx_bytes += (uint32_t)T * W * 4u;
+            }
+        }
+    uint32_t* sdst = raw + fbase;                                  // T : row -> owner << 27 | record index in its inbox
+    uint16_t* order = reinterpret_cast<uint16_t*>(sdst + T);       // T : position sorted by owner -> row
+    if (tid < 8)
+        scnt[tid] = 0;
+    const bool bulk = args.bulk && tile_n == (uint32_t)T && tx_bytes != 0;
+    const uint32_t bar = smem_u32(&bar_mem);
+    if (bulk && tid == 0)
+        mbar_init(bar, 1);
+    __syncthreads();
+    if (bulk)
+        {
+        if (tid == 0)
+            {
+            mbar_expect_tx(bar, tx_bytes);
+            uint32_t fb = (uint32_t)T + SLOT_SKEW;
+            for (int fi = 1; fi < args.nfields; fi++)
+                {
+                const uint32_t W = args.f[fi].words;
+                if (args.f[fi].in == nullptr)
+                    continue;
+                bulk_g2s(smem_u32(raw + fb), args.f[fi].in + tile0 * W, (uint32_t)T * W * 4u, bar);
+                fb += (uint32_t)T * W + SLOT_SKEW;
+                }
+            }
+        }
+    else
+        {
+        uint32_t fb = (uint32_t)T + SLOT_SKEW;
+        for (int fi = 1; fi < args.nfields; fi++)
+            {
+            const uint32_t W = args.f[fi].words;
+            if (args.f[fi].in == nullptr)
+                continue;
+            const uint32_t* in = args.f[fi].in + tile0 * W;
+            const uint32_t total = tile_n * W;
+            for (uint32_t q = tid; q < total; q += NT)
+                raw[fb + q] = __ldg(in + q);
+            fb += (uint32_t)T * W + SLOT_SKEW;
+            }
+        }
+    // rank of every row among the tile's rows for the same owner
+    uint32_t own[PER], rk[PER];
+#pragma unroll
+    for (int k = 0; k < PER; k++)
+        {
+        const uint32_t r = (uint32_t)tid + (uint32_t)k * NT;
+        own[k] = 0;
+        rk[k] = 0;
+        if (r < tile_n)
+            {
+            own[k] = ((key[k] >> L) & bmask) / args.nbr;
+            rk[k] = atomicAdd(&scnt[own[k]], 1u);
+            }
+        }
+    __syncthreads();
+    if (tid < args.nranks)
+        sbase[tid] = scnt[tid] ? atomicAdd(owner_cursor + tid, scnt[tid]) : 0u; // one run per (tile, owner)
+    if (tid == 0)
+        {
+        uint32_t run = 0;
+        for (int o = 0; o < 8; o++)
+            {
+            sofs[o] = run;
+            run += scnt[o];
+            }
+        sofs[8] = run;
+        }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < PER; k++)
+        {
+        const uint32_t r = (uint32_t)tid + (uint32_t)k * NT;
+        if (r < tile_n)
+            {
+            order[sofs[own[k]] + rk[k]] = (uint16_t)r;
+            sdst[r] = (own[k] << 27) | (sbase[own[k]] + rk[k]);
+            raw[r] = key[k];
+            }
+        }
+    if (bulk)
+        {
+        const bool ok = mbar_wait(bar, 0);
+        if (__syncthreads_or(!ok))
+            {
+            if (tid == 0)
+                flag[1] = 3;
+            return;
+            }
+        }
+    else
+        __syncthreads();
+    slot_records_out<NT>(raw, sdst, col, tile0, tile_n, RW, nullptr, args, lane, w, order);
+    }
+
+// ---- distributed reorder, step 2: the slot scatter on records that are already interleaved (the inbox) -----------
+// One bulk copy per tile; bucket = key bits above the slot bits minus this rank's first bucket; positions from the
+// local cursors; records go into the "lines" copy k6_slot_place reads.
+template <int T, int NT>
+__global__ void __launch_bounds__(NT) k6_slot_scatter_rec(const uint32_t* __restrict__ rec, uint64_t n, int L, uint32_t bmask,
+                                                         uint32_t bucket0, uint32_t* __restrict__ cursor, uint32_t cstride,
+                                                         uint32_t* __restrict__ aos, uint32_t* __restrict__ flag,
+                                                         const __grid_constant__ SlotArgs args)
+    {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long bar_mem;
+    __shared__ uint32_t col[SLOT_MAX_ROW_WORDS];
+    uint32_t* rows = reinterpret_cast<uint32_t*>(smem_raw); // T records of RW words
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const uint64_t tile0 = (uint64_t)blockIdx.x * T;
+    const uint32_t tile_n = (uint32_t)((n - tile0) < (uint64_t)T ? (n - tile0) : T);
+    const uint32_t RW = args.row_words;
+    uint32_t* sdst = rows + (size_t)T * RW;
+    if (tid < (int)RW)
+        col[tid] = ((uint32_t)tid << 8) | RW; // column c of record r: rows[c + r * RW]
+    const uint32_t bar = smem_u32(&bar_mem);
+    const uint32_t bytes = tile_n * RW * 4u;
+    const bool bulk = (bytes & 15u) == 0; // tile0 * RW * 4 is a multiple of 16 (T is a multiple of 4)
+    if (bulk && tid == 0)
+        mbar_init(bar, 1);
+    __syncthreads();
+    if (bulk)
+        {
+        if (tid == 0)
+            {
+            mbar_expect_tx(bar, bytes);
+            bulk_g2s(smem_u32(rows), rec + tile0 * RW, bytes, bar);
+            }
+        const bool ok = mbar_wait(bar, 0);
+        if (__syncthreads_or(!ok))
+            {
+            if (tid == 0)
+                flag[1] = 3;
+            return;
+            }
+        }
+    else
+        {
+        for (uint32_t q = tid; q < tile_n * RW; q += NT)
+            rows[q] = __ldg(rec + tile0 * RW + q);
+        __syncthreads();
+        }
+    constexpr int PER = T / NT;
+    uint32_t d[PER];
+#pragma unroll
+    for (int k = 0; k < PER; k++)
+        {
+        const uint32_t r = (uint32_t)tid + (uint32_t)k * NT;
+        d[k] = 0;
+        if (r < tile_n)
+            {
+            const uint32_t bl = ((rows[r * RW] >> L) & bmask) - bucket0;
+            d[k] = (atomicAdd(cursor + (size_t)bl * cstride, 1u) & 4095u) | (bl << 12);
+            }
+        }
+#pragma unroll
+    for (int k = 0; k < PER; k++)
+        sdst[(uint32_t)tid + (uint32_t)k * NT] = d[k];
+    __syncthreads();
+    slot_records_out<NT>(rows, sdst, col, tile0, tile_n, RW, aos, args, lane, w);
     }
 
 // ---- place: one CTA per bucket; slot = key & (CAP-1) is the row's rank among the bucket's (unique) keys ---
@@ -1113,9 +1324,19 @@ int dev_reorder_distributed(uint64_t n_local, const uint32_t* keys, uint64_t out
     while (tile > 512 && ((size_t)in_words + 1) * tile * 4 > 200 * 1024)
         tile /= 2;
 
-    // (2) the shared copy: same size on every rank; reallocation is a collective decision
+    // Two ways to get the records to their owners (same on every rank):
+    //   partition (default for > 1 rank): k6_part_scatter appends every record to the owner's INBOX -- a tile writes
+    //       one contiguous run per owner, which is what NVLink wants -- then the owner runs k6_slot_scatter_rec +
+    //       k6_slot_place on its inbox.  Three passes over the rows, all of them streaming.
+    //   fused (PGSD_B200_DIST_MODE=fused, and always for 1 rank): k6_slot_scatter stores every record directly at its
+    //       place in the owner's bucketed copy.  Two passes, but the link carries single 40-byte stores
+    //       (measured 300 GB/s per direction at 2 GPUs: 3.7 ms against 3.4 ms on one GPU).
+    const char* emode = getenv("PGSD_B200_DIST_MODE");
+    const bool part = G > 1 && !(emode && !strcmp(emode, "fused"));
+    // (2) the shared buffer (inbox / bucketed copy): same size on every rank; reallocation is a collective decision
     const size_t nlines = ((size_t)cap * a.row_words * 4 + 127) / 128;
-    const size_t copy_need = up256((size_t)nbr * nlines * 128) + 256;
+    const size_t lines_bytes = up256((size_t)nbr * nlines * 128) + 256;
+    const size_t copy_need = part ? up256((size_t)nbr * cap * a.row_words * 4) + 256 : lines_bytes;
     bool grow = false;
     for (int p = 0; p < G; p++)
         if (all[(size_t)p * 12 + 2] < copy_need)
@@ -1188,7 +1409,7 @@ int dev_reorder_distributed(uint64_t n_local, const uint32_t* keys, uint64_t out
     const size_t tb = up256((size_t)(nbp + 1) * 4);
     const size_t bb = up256((size_t)(nbr + 2) * 4);
     const size_t cb = up256((size_t)nbp * cstride * 4);
-    const size_t need = 256 + 2 * tb + bb + cb;
+    const size_t need = 256 + 2 * tb + bb + cb + 256 + (part ? lines_bytes : 0);
     bool ws_ok = true;
     if (g_slot_ws_bytes < need)
         {
@@ -1222,6 +1443,8 @@ int dev_reorder_distributed(uint64_t n_local, const uint32_t* keys, uint64_t out
     uint32_t* base = (uint32_t*)(p8 + 256 + tb);
     uint32_t* start = (uint32_t*)(p8 + 256 + tb + bb);
     uint32_t* cursor = (uint32_t*)(p8 + 256 + 2 * tb + bb);
+    uint32_t* owner_cursor = (uint32_t*)(p8 + 256 + 2 * tb + bb + cb);          // 8 words
+    uint32_t* lines_copy = (uint32_t*)(p8 + 256 + 2 * tb + bb + cb + 256);      // partition mode only
 
     trace.mark("peers+workspace");
     // (3) local histogram, counts of all ranks
@@ -1305,21 +1528,62 @@ int dev_reorder_distributed(uint64_t n_local, const uint32_t* keys, uint64_t out
         hbase[i] += hbase[i - 1];
     hbase[nbr + 1] = hbase[nbr];
     *n_out = owned[me];
-    cudaMemcpyAsync(start, hstart.data(), (size_t)nbp * 4, cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(base, hbase.data(), (size_t)(nbr + 1) * 4, cudaMemcpyHostToDevice, st);
-    k6_slot_spread<<<(nbp + 255) / 256, 256, 0, st>>>(start, nbp, cursor, cstride);
-    dev_stats().kernel_launches++;
-
-    trace.mark("tables+H2D");
-    // (4) records to their owners
-    cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess && n_local > 0)
+    cudaError_t e = cudaSuccess;
+    uint32_t hown[8] = { 0 };
+    if (part)
         {
-        const uint32_t tiles_all = (uint32_t)((n_local + tile - 1) / tile);
-        if (tile == 512)
-            e = launch_scatter<512, 128>(n_local, 0, tiles_all, L, bmask, cursor, cstride, (uint32_t*)g_dist_copy, flag, a, in_words, st);
-        else
-            e = launch_scatter<1024, 256>(n_local, 0, tiles_all, L, bmask, cursor, cstride, (uint32_t*)g_dist_copy, flag, a, in_words, st);
+        // where my run starts in every owner's inbox: the rows of lower ranks for that owner come first
+        for (int o = 0; o < G; o++)
+            {
+            const uint32_t b0 = (uint32_t)o * nbr < nb_used ? (uint32_t)o * nbr : nb_used;
+            const uint32_t b1 = b0 + nbr < nb_used ? b0 + nbr : nb_used;
+            for (int p = 0; p < me; p++)
+                {
+                const uint32_t* cp = reinterpret_cast<const uint32_t*>(&call[(size_t)p * cw]);
+                for (uint32_t b = b0; b < b1; b++)
+                    hown[o] += cp[b];
+                }
+            }
+        cudaMemcpyAsync(owner_cursor, hown, sizeof(hown), cudaMemcpyHostToDevice, st);
+        trace.mark("tables+H2D");
+        // (4) records to their owners' inboxes
+        SlotArgs ap = a;
+        ap.nbl = 0;
+        if (n_local > 0)
+            {
+            const size_t smem = ((size_t)in_words + 1) * tile * 4 + SLOT_MAX_FIELDS * SLOT_SKEW * 4 + (size_t)tile * 2;
+            const uint32_t tiles = (uint32_t)((n_local + tile - 1) / tile);
+            if (tile == 512)
+                {
+                cudaFuncSetAttribute(k6_part_scatter<512, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                k6_part_scatter<512, 128><<<tiles, 128, smem, st>>>(n_local, L, bmask, owner_cursor, flag, ap);
+                }
+            else
+                {
+                cudaFuncSetAttribute(k6_part_scatter<1024, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                k6_part_scatter<1024, 256><<<tiles, 256, smem, st>>>(n_local, L, bmask, owner_cursor, flag, ap);
+                }
+            dev_stats().kernel_launches++;
+            e = cudaGetLastError();
+            }
+        }
+    else
+        {
+        cudaMemcpyAsync(start, hstart.data(), (size_t)nbp * 4, cudaMemcpyHostToDevice, st);
+        k6_slot_spread<<<(nbp + 255) / 256, 256, 0, st>>>(start, nbp, cursor, cstride);
+        dev_stats().kernel_launches++;
+        trace.mark("tables+H2D");
+        // (4) records to their places in the owners' bucketed copies
+        e = cudaGetLastError();
+        if (e == cudaSuccess && n_local > 0)
+            {
+            const uint32_t tiles_all = (uint32_t)((n_local + tile - 1) / tile);
+            if (tile == 512)
+                e = launch_scatter<512, 128>(n_local, 0, tiles_all, L, bmask, cursor, cstride, (uint32_t*)g_dist_copy, flag, a, in_words, st);
+            else
+                e = launch_scatter<1024, 256>(n_local, 0, tiles_all, L, bmask, cursor, cstride, (uint32_t*)g_dist_copy, flag, a, in_words, st);
+            }
         }
     cudaMemcpyAsync(g_slot_flag_host, flag, 12, cudaMemcpyDeviceToHost, st);
     uint64_t st4 = 0;
@@ -1349,7 +1613,34 @@ int dev_reorder_distributed(uint64_t n_local, const uint32_t* keys, uint64_t out
         {
         SlotArgs ap = a;
         ap.bulk = 1;
-        k6_slot_place<<<my_b1 - my_b0, cap / 4, place_smem, st>>>(base, L, (const uint32_t*)g_dist_copy, flag, ap);
+        ap.nranks = 1;
+        const uint32_t* bucketed = (const uint32_t*)g_dist_copy;
+        if (part)
+            {
+            // my inbox (owned[me] records, any order) -> bucketed copy, with the cursors starting at 0
+            cudaMemsetAsync(cursor, 0, (size_t)nbr * cstride * 4, st);
+            const int rt = ((size_t)a.row_words + 1) * 1024 * 4 <= 200 * 1024 ? 1024 : 512;
+            const size_t smem = ((size_t)a.row_words + 1) * rt * 4;
+            const uint32_t tiles = (uint32_t)((owned[me] + rt - 1) / rt);
+            if (tiles)
+                {
+                if (rt == 512)
+                    {
+                    cudaFuncSetAttribute(k6_slot_scatter_rec<512, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    k6_slot_scatter_rec<512, 128><<<tiles, 128, smem, st>>>((const uint32_t*)g_dist_copy, owned[me], L, bmask, my_b0,
+                                                                           cursor, cstride, lines_copy, flag, ap);
+                    }
+                else
+                    {
+                    cudaFuncSetAttribute(k6_slot_scatter_rec<1024, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    k6_slot_scatter_rec<1024, 256><<<tiles, 256, smem, st>>>((const uint32_t*)g_dist_copy, owned[me], L, bmask, my_b0,
+                                                                            cursor, cstride, lines_copy, flag, ap);
+                    }
+                dev_stats().kernel_launches++;
+                }
+            bucketed = lines_copy;
+            }
+        k6_slot_place<<<my_b1 - my_b0, cap / 4, place_smem, st>>>(base, L, bucketed, flag, ap);
         dev_stats().kernel_launches++;
         e = cudaGetLastError();
         cudaMemcpyAsync(g_slot_flag_host, flag, 12, cudaMemcpyDeviceToHost, st);

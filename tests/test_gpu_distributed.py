@@ -16,13 +16,17 @@ import dist_reorder_worker as W
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("nprocs", [1, 2, 3, 4, 8])
-def test_reorder_distributed_equals_stable_argsort(lib, nprocs):
+@pytest.mark.parametrize("nprocs,mode", [(1, "partition"), (2, "partition"), (3, "partition"), (4, "partition"), (8, "partition"),
+                                         (2, "fused"), (3, "fused"), (8, "fused")])
+def test_reorder_distributed_equals_stable_argsort(lib, nprocs, mode):
+    """mode: how records reach their owners -- "partition" (runs appended to the owner's inbox, then the local
+    two-pass reorder) or "fused" (every record stored directly at its place in the owner's bucketed copy)."""
     assert lib.pgsd_b200_cuda_available() == 1, "no CUDA device: the device path has no CPU fallback"
     with tempfile.TemporaryDirectory() as d:
-        seg = f"/pgsd_dist_{os.getpid()}_{nprocs}"
+        seg = f"/pgsd_dist_{os.getpid()}_{nprocs}_{mode}"
+        env = dict(os.environ, PGSD_B200_DIST_MODE=mode)
         procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "dist_reorder_worker.py"), str(r), str(nprocs), seg, d],
-                                  stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(nprocs)]
+                                  env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(nprocs)]
         outs = []
         for p in procs:
             try:
