@@ -163,8 +163,9 @@ int pgsd_b200_reorder_host(uint64_t n, const uint32_t* keys_host, uint32_t* keys
    Rank r ends up with the rows whose ids lie in [*id_first, *id_first + S), S = ceil(ceil(N / C) / ranks) * C
    with C = 1024 (2048 / 4096 for more than 32 Mi / 64 Mi rows in total), in id order: *n_out rows written to
    keys_sorted_device and to every fields[i].out (capacity out_capacity rows each; S always suffices).
-   The exchange is not a separate step: the scatter kernel stores every record straight into the owner's
-   memory (CUDA IPC mapping, i.e. NVLink) and the owner finishes its buckets locally.
+   The exchange is not a separate collective: a kernel stores every record straight into the owner's memory
+   (CUDA IPC mapping, i.e. NVLink) -- appended to the owner's inbox in contiguous runs (default) or, with
+   PGSD_B200_DIST_MODE=fused, at its final place in the owner's bucketed copy -- and the owner finishes locally.
    Returns 0, a negative pgsd error, or 1 on EVERY rank when the ids are not unique or not all below
    ceil(N / C) * C (dense ids 0..N-1 qualify): nothing was written, gather the frame to one GPU and use
    pgsd_b200_reorder_device.  row_bytes must be multiples of 4; keys 16-byte aligned. */

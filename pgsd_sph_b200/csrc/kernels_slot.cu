@@ -1140,16 +1140,17 @@ int dev_reorder_slot(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, ui
 
 // ---- distributed reorder: ONE frame whose rows are partitioned over the ranks (config 3 read-back) -----------
 // "GPU g loads file partition g; destination GPU = id / ceil(N/G); one all-to-all of
-// 40-byte rows, then local sort + gather".  Here the all-to-all is not a separate step: k6_slot_scatter writes
-// every record straight into the owner's interleaved copy -- its own memory or a CUDA IPC mapping of the peer's,
-// i.e. plain stores over NVLink -- and each owner then runs the unchanged k6_slot_place on its buckets.
-//   1 all-gather  n_local, output capacity, size + IPC handle of the shared copy (-> geometry, same on every rank;
-//   2             mappings are cached between calls; a second exchange only when the copy has to grow)
-//   3 k6_slot_hist on the local keys; all-gather of the bucket counts (+ the range flag): every rank now knows
-//     where its records start inside every bucket (sum of the counts of lower ranks: cursors need no remote
-//     atomics), how many rows every rank will own, and whether a bucket overflows -- identical decisions
-//   4 k6_slot_scatter (local atomics, local + remote stores), stream sync, barrier all-gather
-//   5 k6_slot_place on the owned buckets, all-gather of the duplicate flags
+// 40-byte rows, then local sort + gather".  Here the all-to-all is not a separate collective: kernels store the
+// records straight into the owner's memory -- its own, or a CUDA IPC mapping of the peer's, i.e. plain stores over
+// NVLink -- and each owner finishes its buckets locally.
+//   1 all-gather  n_local, output capacity, size + IPC handle of the shared buffer (-> geometry, same on every rank;
+//                 mappings are cached between calls; a second exchange only when the buffer has to grow)
+//   2 k6_slot_hist on the local keys; all-gather of the bucket counts (+ the range flag): every rank now knows
+//     where its records start at every destination (sum of the counts of lower ranks: no remote atomics), how
+//     many rows every rank will own, and whether a bucket overflows -- identical decisions everywhere
+//   3 records to their owners: k6_part_scatter into the owners' inboxes ("partition", default) or k6_slot_scatter
+//     into the owners' bucketed copies ("fused"); stream sync; barrier all-gather
+//   4 owner: [partition: k6_slot_scatter_rec inbox -> bucketed copy] k6_slot_place; all-gather of the duplicate flags
 // Requires unique ids below ceil(N / 2^L) * 2^L (dense ids 0..N-1 qualify); otherwise every rank returns 1
 // and the caller gathers the frame to one GPU and uses pgsd_b200_reorder_device.
 static void* g_dist_copy = nullptr; // this rank's part of the interleaved copy (IPC-exported)
