@@ -326,6 +326,33 @@ def reorder_by_id_distributed(ids, arrays):
     return int(id_first.value), trim(sorted_ids), {k: trim(v) for k, v in outs.items()}
 
 
+#: per-particle chunks of the SPH configs and their row widths
+SPH_FIELDS = {'position': 3, 'velocity': 3, 'typeid': 1, 'density': 1, 'pressure': 1}
+
+
+def read_frame_distributed(file, frame, fields=None):
+    """Config 3 read-back, end to end: one frame, every rank reads ITS row slice of each per-particle chunk from
+    the file straight into device memory (``read_chunk(..., r_all=True, device=True)``, the row-sliced read of
+    pgsd.c:2497-2508 with the split rule of benchmark-read.cc:64-76) and the frame is put into particle-ID order
+    across the GPUs by :py:func:`reorder_by_id_distributed`.
+
+    ``file``: a :py:class:`pgsd_sph_b200.fl.PGSDFile` opened for reading on every rank; ``fields``: dict
+    ``name -> M`` of ``particles/<name>`` chunks (default :py:data:`SPH_FIELDS`).  Returns ``(first_id, ids,
+    arrays)``: this rank's share of the ID-ordered frame as DeviceArrays.  Collective.
+    """
+    from . import synth
+    lib = _lib.load()
+    fields = dict(SPH_FIELDS if fields is None else fields)
+    n = int(file.read_chunk(frame=frame, name='particles/N')[0])
+    rank, nranks = lib.pgsd_b200_comm_rank(), lib.pgsd_b200_comm_size()
+    rows = synth.split_rows(n, nranks)
+    start, mine = synth.row_starts(rows)[rank], rows[rank]
+    ids = file.read_chunk(frame=frame, name=ID_CHUNK, N=mine, M=1, offset=start, r_all=True, device=True)
+    arrays = {k: file.read_chunk(frame=frame, name='particles/' + k, N=mine, M=m, offset=start, r_all=True, device=True)
+              for k, m in fields.items()}
+    return reorder_by_id_distributed(ids.reshape(mine), {k: (v if fields[k] > 1 else v.reshape(mine)) for k, v in arrays.items()})
+
+
 class HOOMDTrajectory(object):
     """Read and write hoomd pgsd files (ref: hoomd.py:519-941).
 

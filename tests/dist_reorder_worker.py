@@ -69,6 +69,15 @@ def main():
     first, sid, out = hoomd.reorder_by_id_distributed(DeviceArray.from_numpy(ids[lo:lo + cnt]),
                                                       {"pos": DeviceArray.from_numpy(pos[lo:lo + cnt])})
     np.savez(os.path.join(outdir, f"rank{rank}_pywrap.npz"), id_first=first, ids=sid.to_numpy(), pos=out["pos"].to_numpy())
+    # config 3 read-back end to end: every rank reads its row slice of a file (written by the parent test) straight
+    # into device memory, then the distributed reorder
+    path = os.path.join(outdir, "frame.gsd")
+    if os.path.exists(path):
+        from pgsd_sph_b200 import fl
+        with fl.open(path, 'r', 'pgsd-b200', 'hoomd', [1, 4]) as f:
+            first, sid, out = hoomd.read_frame_distributed(f, 0)
+        np.savez(os.path.join(outdir, f"rank{rank}_file.npz"), id_first=first, ids=sid.to_numpy(),
+                 **{k: v.to_numpy() for k, v in out.items()})
     lib.pgsd_b200_comm_finalize()
     print(f"rank {rank} ok")
 

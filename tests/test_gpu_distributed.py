@@ -23,6 +23,16 @@ def test_reorder_distributed_equals_stable_argsort(lib, nprocs, mode):
     two-pass reorder) or "fused" (every record stored directly at its place in the owner's bucketed copy)."""
     assert lib.pgsd_b200_cuda_available() == 1, "no CUDA device: the device path has no CPU fallback"
     with tempfile.TemporaryDirectory() as d:
+        # a frame file for the end-to-end leg (written here by one rank: whole chunks, like any reference file)
+        from pgsd_sph_b200 import fl, synth
+        FILE_N = 123457
+        frame = synth.make_frame(FILE_N, 3)
+        with fl.open(os.path.join(d, "frame.gsd"), 'w', 'pgsd-b200', 'hoomd', [1, 4]) as f:
+            for k, a in synth.frame_scalars(FILE_N, 0):
+                f.write_chunk(k, a, write_all=False)
+            for k, a in frame.items():
+                f.write_chunk(k, a)
+            f.end_frame()
         seg = f"/pgsd_dist_{os.getpid()}_{nprocs}_{mode}"
         env = dict(os.environ, PGSD_B200_DIST_MODE=mode)
         procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "dist_reorder_worker.py"), str(r), str(nprocs), seg, d],
@@ -72,3 +82,12 @@ def test_reorder_distributed_equals_stable_argsort(lib, nprocs, mode):
         assert np.concatenate([x["ids"] for x in res]).tobytes() == ids[o].tobytes()
         assert np.concatenate([x["pos"] for x in res]).tobytes() == pos[o].tobytes()
         assert all(len(x["ids"]) == 0 or x["ids"][0] == x["id_first"] for x in res)
+        # file -> row-sliced device reads on every rank -> distributed reorder
+        ids = frame['log/particles/id'].reshape(-1)
+        o = np.argsort(ids, kind='stable')
+        res = [np.load(os.path.join(d, f"rank{r}_file.npz")) for r in range(nprocs)]
+        assert np.concatenate([x["ids"] for x in res]).tobytes() == ids[o].tobytes()
+        for name in ("position", "velocity", "typeid", "density", "pressure"):
+            want = frame['particles/' + name]
+            got = np.concatenate([x[name] for x in res])
+            assert got.tobytes() == want[o].tobytes(), name
