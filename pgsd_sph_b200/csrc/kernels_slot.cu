@@ -42,6 +42,11 @@
 // scatter after it: 0.82 ms, because records then no longer arrive in position order and half-filled lines
 // are evicted and fetched again (DRAM 1.34 GB read / 0.99 GB written instead of 0.74 / 0.67).
 //
+// Distributed (one frame partitioned over the ranks, pgsd_b200_reorder_distributed, bottom of this file): the same
+// kernels on each owner's share, fed by k6_part_scatter (records appended to the owner's inbox in peer memory as
+// contiguous runs) + k6_slot_scatter_rec (the scatter above on already interleaved records), or -- fused mode --
+// by k6_slot_scatter storing straight into the owners' bucketed copies.
+//
 // sm_100a only (cp.async.bulk + mbarrier).  No CPU fallback.
 #include "device_internal.h"
 
