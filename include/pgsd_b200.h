@@ -145,9 +145,13 @@ int pgsd_b200_sort_ids(uint64_t n, const uint32_t* keys_device, uint32_t* keys_s
 int pgsd_b200_gather(uint64_t n, const uint32_t* perm_device, int nfields,
                      const struct pgsd_b200_field* fields_device, void* cuda_stream);
 
-/* K4+K5 on device-resident data.  Frames of >= 1 Mi rows (PGSD_B200_BUCKET_MIN_ROWS) first get a
-   bucket pass: rows grouped by the top key bits into a workspace copy (n * (row bytes + 8) bytes of
-   device memory, cached between calls) so that the gather is L2-local. */
+/* K4+K5 on device-resident data.  Unique keys with at most 27 varying bits (particle ids) and word-sized
+   fields of at most 31 words per row in total take the slot path: two passes over interleaved records, no
+   ranking (kernels_slot.cu; workspace n * (row bytes + 4), cached between calls); the call then returns
+   after the stream has been synchronised, because a device flag decides whether duplicates were found.
+   Anything else takes the stable general path: frames of >= 1 Mi rows (PGSD_B200_BUCKET_MIN_ROWS) first
+   get a bucket pass -- rows grouped by the top key bits into a workspace copy (n * (row bytes + 8) bytes)
+   so that the gather is L2-local -- then LSD passes on (key, index) and the gather. */
 int pgsd_b200_reorder_device(uint64_t n, const uint32_t* keys_device, uint32_t* keys_sorted_device,
                              uint32_t* perm_device, int nfields,
                              const struct pgsd_b200_field* fields_device, void* cuda_stream);
