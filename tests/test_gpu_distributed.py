@@ -12,6 +12,7 @@ import pytest
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 import dist_reorder_worker as W
+from oracle import reorder_oracle
 
 pytestmark = pytest.mark.gpu
 
@@ -61,6 +62,12 @@ def test_reorder_distributed_equals_stable_argsort(lib, nprocs, mode):
                 assert rcs == {1}, (name, rcs)
                 continue
             assert rcs == {0}, (name, rcs)
+            shares = reorder_oracle.reorder_distributed(ids, {"pos": pos, "tag": tag, "dens": dens}, nprocs)
+            for r, (x, (first, sid, exp)) in enumerate(zip(res, shares)):     # rank by rank against the oracle's shares
+                assert int(x["id_first"]) == first and int(x["n_out"]) == len(sid), (name, r)
+                assert x["ids"].tobytes() == sid.tobytes(), (name, r)
+                for k in ("pos", "tag", "dens"):
+                    assert x[k].tobytes() == exp[k].tobytes(), (name, r, k)
             o = np.argsort(ids, kind='stable')
             got_ids = np.concatenate([x["ids"] for x in res])
             assert got_ids.tobytes() == ids[o].tobytes(), name

@@ -64,3 +64,29 @@ def test_known_layout_appendix_b(golden):
     sizes = {P: os.path.getsize(os.path.join(golden, f"hoomd_p{P}.gsd")) for P in (1, 2, 3, 8)}
     per_rank = sizes[2] - sizes[1]
     assert per_rank > 0 and sizes[3] - sizes[2] == per_rank and sizes[8] - sizes[1] == 7 * per_rank
+
+
+def test_distributed_ownership_oracle_matches_the_library_plan():
+    """The numpy restatement of the distributed reorder's ownership rule (oracle/reorder_oracle.py) and the
+    library's host-only plan function agree for every frame size / rank count tried, and the oracle's shares
+    tile the sorted frame."""
+    import ctypes as C
+    import numpy as np
+    from oracle import reorder_oracle
+    from pgsd_sph_b200 import _lib
+    lib = _lib.load()
+    for n in (1, 2, 1023, 1024, 1025, 5000, 123457, 300001, 1 << 20, (1 << 25) - 1, 1 << 25, (1 << 25) + 1,
+              64 << 20, (64 << 20) + 1, 100 << 20, (1 << 27)):
+        for ranks in (1, 2, 3, 4, 5, 8):
+            S, cap = reorder_oracle.distributed_ownership(n, ranks)
+            for r in range(ranks):
+                first, rows = C.c_uint64(), C.c_uint64()
+                assert lib.pgsd_b200_reorder_distributed_plan(n, ranks, r, C.byref(first), C.byref(rows)) == 0
+                assert (first.value, rows.value) == (r * S, S), (n, ranks, r)
+    rng = np.random.default_rng(5)
+    ids = rng.permutation(70001).astype(np.uint32)
+    pos = rng.standard_normal((70001, 3)).astype(np.float32)
+    shares = reorder_oracle.reorder_distributed(ids, {"pos": pos}, 3)
+    assert np.array_equal(np.concatenate([s[1] for s in shares]), np.arange(70001, dtype=np.uint32))
+    assert np.concatenate([s[2]["pos"] for s in shares]).tobytes() == pos[np.argsort(ids, kind='stable')].tobytes()
+    assert all(len(s[1]) == 0 or (s[1][0] >= s[0] and s[1][-1] < s[0] + 23552) for s in shares)   # S = ceil(69 / 3) * 1024
