@@ -222,6 +222,10 @@ int pgsd_b200_reorder_profiling(int on);
 int pgsd_b200_pack_profiling(int on);
 int pgsd_b200_pack_last_ms(float* ms);
 int pgsd_b200_reorder_phase_ms(float* out4);
+/* Device self-tests of failure paths that valid inputs never reach.  which = 0: a kernel waits on an mbarrier
+   whose bulk copy never arrives; returns 0 when the bounded wait gave up and reported it (the reorder kernels'
+   "a bulk copy did not complete" path), > 0 otherwise. */
+int pgsd_b200_selftest(int which);
 
 #ifdef __cplusplus
 }

@@ -198,6 +198,7 @@ SIGNATURES = {
     "pgsd_b200_pack_last_ms": (_i, [C.POINTER(C.c_float)]),
     "pgsd_b200_reorder_profiling": (_i, [_i]),
     "pgsd_b200_reorder_phase_ms": (_i, [C.POINTER(C.c_float)]),
+    "pgsd_b200_selftest": (_i, [_i]),
 }
 
 _lib = None

@@ -357,5 +357,11 @@ int pgsd_b200_reorder_profiling(int on)
     return 0;
     }
 int pgsd_b200_reorder_phase_ms(float* out4) { return out4 ? dev_reorder_phase_ms(out4) : PGSD_ERROR_INVALID_ARGUMENT; }
+int pgsd_b200_selftest(int which)
+    {
+    if (which == 0)
+        return dev_selftest_mbar_timeout();
+    return PGSD_ERROR_INVALID_ARGUMENT;
+    }
 
 } // extern "C"

@@ -109,6 +109,8 @@ int dev_reorder_distributed(uint64_t n_local, const uint32_t* keys, uint64_t out
                             uint64_t* id_first, uint32_t* keys_sorted, int nfields, const ReorderField* fields,
                             void* stream);
 
+int dev_selftest_mbar_timeout(); // kernels_cluster.cu; 0: the bounded mbarrier wait timed out and was reported
+
 // phase timing of the last bucketed reorder (CUDA events): census, bucket pass, pair passes, gather
 void dev_pack_profiling(bool on); // K1 launch of the last frame write
 int dev_pack_last_ms(float* ms);

@@ -18,8 +18,15 @@ int dev_reorder_rows(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, ui
 // kernels_slot.cu: reorder for unique keys; *done = 0 -> not applicable / duplicates, run the general path
 void slot_release_workspace();
 int dev_reorder_slot(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, uint32_t* perm, int nfields,
-                     const ReorderField* fields, int topbit, int guessed, void* stream, int* done, int* out_of_range,
-                     void (*mark)(int, cudaStream_t));
+                     const ReorderField* fields, int topbit, int guessed, uint32_t key_const, void* stream, int* done,
+                     int* out_of_range, void (*mark)(int, cudaStream_t));
+
+// kernels_cluster.cu: coarse partition + cluster placement for large frames with unique keys; *handled = 0 ->
+// geometry does not fit, nothing launched
+void cluster_release_workspace();
+int dev_reorder_cluster(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, uint32_t* perm, int nfields,
+                        const ReorderField* fields, int topbit, uint32_t key_const, void* stream, int* done,
+                        int* out_of_range, void (*mark)(int, cudaStream_t), int* handled);
 
 // pgsd_type codes (include/pgsd.h; ref: /root/reference/pgsd/pgsd/pgsd.h:38-69)
 enum : int

@@ -32,7 +32,7 @@
 // caller falls back to the stable general path of kernels_sort.cu.
 //
 // Measured on B200, 16 Mi particles (profiles/README.md, r2): place 0.215 ms = 0.95 of the measured HBM
-// copy rate; scatter 0.50 ms, which decomposes (PGSD_B200_SLOT_DEBUG timing experiments, flat layout) into
+// copy rate; scatter 0.50 ms, which decomposes (round-1 timing experiments, profiles/r2_time_slot_scatter_decomposition.txt) into
 // staging 0.12 + cursor atomics 0.16-0.20 + record stores 0.11 (+ 0.17 when they go to their scattered
 // places) -- additive although no unit is above 35 % busy in ncu: DRAM spends its time opening rows for the
 // write-backs, not transferring.  Tried without gain: a persistent double-buffered variant that overlaps
@@ -48,7 +48,7 @@
 // by k6_slot_scatter storing straight into the owners' bucketed copies.
 //
 // sm_100a only (cp.async.bulk + mbarrier).  No CPU fallback.
-#include "device_internal.h"
+#include "slot_common.cuh"
 
 #include "comm.h"
 
@@ -59,86 +59,9 @@
 
 namespace pgsdb
 {
+using namespace slotk;
 namespace
     {
-constexpr int SLOT_MAX_FIELDS = 18;    // key + 16 caller fields + original index
-constexpr int SLOT_MAX_ROW_WORDS = 32; // one warp store covers >= 1 row
-constexpr int SLOT_MIN_BITS = 10;
-constexpr int SLOT_MAX_BITS = 12;
-constexpr int SLOT_MAX_BUCKET_BITS = 15; // 32768 buckets: 128 KB histogram in shared memory
-
-struct SlotField
-    {
-    const uint32_t* in; // n rows of `words` words; NULL: the row's original index
-    uint32_t* out;      // destination of the reordered field; NULL: not wanted
-    uint32_t words;
-    uint32_t off;       // word offset inside the interleaved row
-    };
-struct SlotArgs
-    {
-    SlotField f[SLOT_MAX_FIELDS];
-    int nfields;
-    uint32_t row_words;
-    int bulk; // every input is 16-byte aligned: full tiles are staged with cp.async.bulk
-    uint32_t nbl; // 0: buckets are contiguous in the interleaved copy ("flat").  nb: "lines" layout -- 128-byte line j of
-                  // bucket b lives at line j * nb + b, so that the lines the buckets are currently filling (about the
-                  // same j for all of them) form one compact, advancing window instead of nb windows spread over the
-                  // whole copy: the L2 write-backs then fall into few open DRAM rows
-    int ushift; // "lines" layout: log2 of the interleaving unit in bytes (7: 128-byte lines)
-    // distributed reorder: rank `o` owns the buckets [o * nbr, (o + 1) * nbr); peer[o] is its interleaved copy
-    // (own memory, or a CUDA IPC mapping of the owner's memory: the record stores then travel over NVLink)
-    uint32_t* peer[8];
-    uint32_t nbr;
-    int nranks; // 1: single-GPU reorder, peer[] unused
-    int debug; // timing experiments only (results are wrong): 1 = no atomics, identity positions; 2 = atomics, identity
-               // positions; 3 = atomics, nothing written; 4 = staging only
-    };
-
-// ---- PTX wrappers: mbarrier + 1-D bulk copy global -> shared (TMA engine) ---------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p)
-    {
-    return (uint32_t)__cvta_generic_to_shared(p);
-    }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
-    {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
-    {
-    unsigned long long state;
-    asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 %0, [%1], %2;"
-                 : "=l"(state)
-                 : "r"(bar), "r"(bytes)
-                 : "memory");
-    (void)state;
-    }
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
-    {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-    }
-// Waits for phase `parity`; gives up after ~2 s worth of cycles so that a lost copy cannot hang the GPU.
-__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity)
-    {
-    const long long t0 = clock64();
-    for (;;)
-        {
-        uint32_t done;
-        asm volatile("{\n\t.reg .pred p;\n\t"
-                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                     "selp.b32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done)
-                     : "r"(bar), "r"(parity)
-                     : "memory");
-        if (done)
-            return true;
-        if (clock64() - t0 > 4000000000ll)
-            return false;
-        }
-    }
-
 // flag words (device): [2] set by k6_slot_hist: a key lies outside the range guessed from n
 //                      [0] set by k6_slot_scan: [2], or a bucket holds more than CAP keys (duplicate ids)
 //                      [1] set by k6_slot_place: 1 = two rows of a bucket share a slot (duplicate ids),
@@ -269,111 +192,10 @@ __global__ void __launch_bounds__(1024) k6_slot_scan(const uint32_t* __restrict_
         }
     }
 
-// records out: a group of lanes writes one record (consecutive words), G records per warp store
-// order != NULL: the loop runs over tile positions j sorted by destination and row = order[j], so that the records
-// of one warp store are neighbours at their destination (partition by owner: long contiguous runs).
-template <int NT>
-__device__ __forceinline__ void slot_records_out(const uint32_t* __restrict__ raw, const uint32_t* __restrict__ sdst,
-                                                 const uint32_t* __restrict__ col, uint64_t tile0, uint32_t tile_n,
-                                                 uint32_t RW, uint32_t* __restrict__ aos, const SlotArgs& args, int lane, int w,
-                                                 const uint16_t* __restrict__ order = nullptr)
-    {
-    constexpr uint32_t NW = NT / 32;
-    constexpr int U = 4;
-    if ((RW & 1u) == 0)
-        {
-        const uint32_t R2 = RW / 2, G = 32u / R2;
-        const uint32_t g = (uint32_t)lane / R2, c2 = (uint32_t)lane - g * R2;
-        if (g < G)
-            {
-            const uint32_t ca = col[2 * c2], cb = col[2 * c2 + 1];
-            const uint32_t Wa = ca & 255u, fa = ca >> 8, Wb = cb & 255u, fb = cb >> 8;
-            uint2* aos2 = reinterpret_cast<uint2*>(aos);
-            const uint32_t step = NW * G;
-            for (uint32_t r0 = (uint32_t)w * G + g; r0 < tile_n; r0 += step * U)
-                {
-                uint32_t dd[U];
-                uint2 v[U];
-#pragma unroll
-                for (int u = 0; u < U; u++)
-                    {
-                    const uint32_t j = r0 + (uint32_t)u * step;
-                    if (j < tile_n)
-                        {
-                        const uint32_t r = order ? order[j] : j;
-                        dd[u] = sdst[r];
-                        v[u].x = Wa ? raw[fa + r * Wa] : (uint32_t)(tile0 + r);
-                        v[u].y = Wb ? raw[fb + r * Wb] : (uint32_t)(tile0 + r);
-                        }
-                    }
-#pragma unroll
-                for (int u = 0; u < U; u++)
-                    if (r0 + (uint32_t)u * step < tile_n)
-                        {
-                        if (args.nbl)
-                            {
-                            const uint32_t o = (dd[u] & 4095u) * (RW * 4u) + c2 * 8u;
-                            const uint64_t at = ((uint64_t)((o >> args.ushift) * args.nbl + ((dd[u] >> 12) & 32767u)) << args.ushift) + (o & ((1u << args.ushift) - 1u));
-                            unsigned char* copy = reinterpret_cast<unsigned char*>(args.nranks > 1 ? args.peer[dd[u] >> 27] : aos);
-                            *reinterpret_cast<uint2*>(copy + at) = v[u];
-                            }
-                        else if (args.nranks > 1) // record index in the owner's inbox
-                            reinterpret_cast<uint2*>(args.peer[dd[u] >> 27])[(uint64_t)(dd[u] & 0x7ffffffu) * R2 + c2] = v[u];
-                        else
-                            aos2[(uint64_t)dd[u] * R2 + c2] = v[u];
-                        }
-                }
-            }
-        }
-    else
-        {
-        const uint32_t G = 32u / RW;
-        const uint32_t g = (uint32_t)lane / RW, c = (uint32_t)lane - g * RW;
-        if (g < G)
-            {
-            const uint32_t cc = col[c];
-            const uint32_t W = cc & 255u, fb = cc >> 8;
-            const uint32_t step = NW * G;
-            for (uint32_t r0 = (uint32_t)w * G + g; r0 < tile_n; r0 += step * U)
-                {
-                uint32_t dd[U], v[U];
-#pragma unroll
-                for (int u = 0; u < U; u++)
-                    {
-                    const uint32_t j = r0 + (uint32_t)u * step;
-                    if (j < tile_n)
-                        {
-                        const uint32_t r = order ? order[j] : j;
-                        dd[u] = sdst[r];
-                        v[u] = W ? raw[fb + r * W] : (uint32_t)(tile0 + r);
-                        }
-                    }
-#pragma unroll
-                for (int u = 0; u < U; u++)
-                    if (r0 + (uint32_t)u * step < tile_n)
-                        {
-                        if (args.nbl)
-                            {
-                            const uint32_t o = (dd[u] & 4095u) * (RW * 4u) + c * 4u;
-                            const uint64_t at = ((uint64_t)((o >> args.ushift) * args.nbl + ((dd[u] >> 12) & 32767u)) << args.ushift) + (o & ((1u << args.ushift) - 1u));
-                            unsigned char* copy = reinterpret_cast<unsigned char*>(args.nranks > 1 ? args.peer[dd[u] >> 27] : aos);
-                            *reinterpret_cast<uint32_t*>(copy + at) = v[u];
-                            }
-                        else if (args.nranks > 1)
-                            args.peer[dd[u] >> 27][(uint64_t)(dd[u] & 0x7ffffffu) * RW + c] = v[u];
-                        else
-                            aos[(uint64_t)dd[u] * RW + c] = v[u];
-                        }
-                }
-            }
-        }
-    }
-
 // ---- scatter: every row to the next free position of its bucket, as one interleaved record -------------
 // Field tiles sit field-major in shared memory, tile i shifted by 4 * i words so that the columns of one
 // record fall into different banks.  The keys (field 0) are loaded straight into registers: their atomics
 // are in flight while the TMA engine brings the payload tiles.
-constexpr uint32_t SLOT_SKEW = 4; // words; keeps every tile 16-byte aligned for the bulk copies
 
 template <int T, int NT>
 __global__ void __launch_bounds__(NT) k6_slot_scatter(uint64_t n, uint32_t tile_first, int L, uint32_t bmask, uint32_t* __restrict__ cursor,
@@ -464,25 +286,18 @@ __global__ void __launch_bounds__(NT) k6_slot_scatter(uint64_t n, uint32_t tile_
         d[k] = 0;
         if (r < tile_n)
             {
-            if (args.debug == 1 || args.debug == 4)
-                d[k] = (uint32_t)(tile0 + r);
-            else
+            const uint32_t b = (key[k] >> L) & bmask;
+            d[k] = atomicAdd(cursor + (size_t)b * cstride, 1u);
+            if (args.nbl)
                 {
-                const uint32_t b = (key[k] >> L) & bmask;
-                d[k] = atomicAdd(cursor + (size_t)b * cstride, 1u);
-                if (args.nbl)
+                // position inside the bucket (< 4096), the bucket (< 32768) and, distributed, its owner
+                uint32_t owner = 0, bl = b;
+                if (args.nranks > 1)
                     {
-                    // position inside the bucket (< 4096), the bucket (< 32768) and, distributed, its owner
-                    uint32_t owner = 0, bl = b;
-                    if (args.nranks > 1)
-                        {
-                        owner = b / args.nbr;
-                        bl = b - owner * args.nbr;
-                        }
-                    d[k] = (d[k] & 4095u) | (bl << 12) | (owner << 27);
+                    owner = b / args.nbr;
+                    bl = b - owner * args.nbr;
                     }
-                if (args.debug == 2 || args.debug == 3)
-                    d[k] = (uint32_t)(tile0 + r) + (d[k] >> 31);
+                d[k] = (d[k] & 4095u) | (bl << 12) | (owner << 27);
                 }
             }
         }
@@ -506,12 +321,6 @@ __global__ void __launch_bounds__(NT) k6_slot_scatter(uint64_t n, uint32_t tile_
     else
         __syncthreads();
 
-    if (args.debug >= 3) // timing experiments: no records written
-        {
-        if (sdst[tid] == 0xffffffffu)
-            aos[tid] = raw[tid];
-        return;
-        }
     // (3) records out
     slot_records_out<NT>(raw, sdst, col, tile0, tile_n, RW, aos, args, lane, w);
     }
@@ -899,6 +708,7 @@ void dist_release_workspace();
 void slot_release_workspace()
     {
     dist_release_workspace();
+    cluster_release_workspace();
     if (g_slot_ws)
         cudaFree(g_slot_ws);
     g_slot_ws = nullptr;
@@ -943,14 +753,22 @@ static cudaError_t launch_scatter(uint64_t n, uint32_t tile_first, uint32_t tile
 // back).  *done = 0: not applicable or duplicate keys found -- the caller must run the general path (inputs
 // are untouched).  phase: optional cudaEvent_t[2] recorded after the scatter and after the placement.
 int dev_reorder_slot(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, uint32_t* perm, int nfields,
-                     const ReorderField* fields, int topbit, int guessed, void* stream_v, int* done, int* out_of_range,
-                     void (*mark)(int, cudaStream_t))
+                     const ReorderField* fields, int topbit, int guessed, uint32_t key_const, void* stream_v, int* done,
+                     int* out_of_range, void (*mark)(int, cudaStream_t))
     {
     *done = 0;
     *out_of_range = 0;
     const char* en = getenv("PGSD_B200_SLOT");
     if (en && en[0] == '0')
         return 0;
+    // large frames: coarse partition + cluster placement (kernels_cluster.cu), two passes without per-row atomics
+        {
+        int handled = 0;
+        const int rc = dev_reorder_cluster(n, keys, keys_sorted, perm, nfields, fields, topbit, guessed ? 0u : key_const, stream_v, done,
+                                           out_of_range, mark, &handled);
+        if (rc != 0 || handled)
+            return rc;
+        }
     if (n == 0 || n >= 0xffffffffull || nfields + 2 > SLOT_MAX_FIELDS || keys_sorted == keys)
         return 0;
     cudaStream_t st = (cudaStream_t)stream_v;
@@ -991,8 +809,6 @@ int dev_reorder_slot(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, ui
     a.nranks = 1;
     const char* eb = getenv("PGSD_B200_SLOT_BULK");
     a.bulk = (aligned && !(eb && eb[0] == '0')) ? 1 : 0;
-    const char* ed = getenv("PGSD_B200_SLOT_DEBUG");
-    a.debug = ed ? atoi(ed) : 0;
     SlotArgs a_place = a; // the interleaved copy is always 16-byte aligned
     a_place.bulk = !(eb && eb[0] == '0') ? 1 : 0;
 
@@ -1138,8 +954,6 @@ int dev_reorder_slot(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, ui
         }
     *done = (g_slot_flag_host[0] == 0 && g_slot_flag_host[1] == 0) ? 1 : 0;
     *out_of_range = g_slot_flag_host[2] != 0 ? 1 : 0;
-    if (a.debug)
-        *done = 1; // timing experiments: the (wrong) result is kept
     return 0;
     }
 

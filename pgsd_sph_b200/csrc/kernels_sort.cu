@@ -1382,6 +1382,7 @@ struct KeyPlan
     int passes[4];
     int npass;
     int topbit; // keys differ only in bits [0, topbit)
+    uint32_t key_const; // the bits all keys share at and above `topbit`
     };
 static int key_census(uint64_t n, const uint32_t* keys, const PassTables& t, cudaStream_t st, KeyPlan* plan)
     {
@@ -1419,6 +1420,7 @@ static int key_census(uint64_t n, const uint32_t* keys, const PassTables& t, cud
             plan->topbit = 8 * b + bits_b;
             }
         }
+    plan->key_const = plan->topbit >= 32 ? 0u : (host[1] & ~((1u << plan->topbit) - 1u));
     return 0;
     }
 
@@ -1630,7 +1632,7 @@ static int reorder_try_slot(uint64_t n, const uint32_t* keys, uint32_t* keys_sor
             phase_mark(0, st);
             phase_mark(1, st);
             }
-        if ((rc = dev_reorder_slot(n, keys, keys_sorted, perm, nfields, fields, tg, 1, stream_v, done, &miss, timed ? slot_mark : nullptr)) != 0)
+        if ((rc = dev_reorder_slot(n, keys, keys_sorted, perm, nfields, fields, tg, 1, 0u, stream_v, done, &miss, timed ? slot_mark : nullptr)) != 0)
             return rc;
         if (*done || !miss)
             return 0; // finished, or not applicable / duplicates: a measured range would not change that
@@ -1651,7 +1653,7 @@ static int reorder_try_slot(uint64_t n, const uint32_t* keys, uint32_t* keys_sor
         phase_mark(1, st);
     if (plan.npass == 0)
         return 0; // all keys equal: the caller's identity path
-    return dev_reorder_slot(n, keys, keys_sorted, perm, nfields, fields, plan.topbit, 0, stream_v, done, &miss, timed ? slot_mark : nullptr);
+    return dev_reorder_slot(n, keys, keys_sorted, perm, nfields, fields, plan.topbit, 0, plan.key_const, stream_v, done, &miss, timed ? slot_mark : nullptr);
     }
 
 static uint64_t slot_min_rows()

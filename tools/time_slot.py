@@ -10,27 +10,21 @@ from pgsd_sph_b200.devmem import DeviceArray
 lib = _lib.load(); _lib.check(lib.pgsd_b200_device_init(0), "init")
 PEAK = 6546.6
 t = C.c_void_p(); lib.pgsd_b200_timer_create(C.byref(t))
-KNOBS = ["PGSD_B200_SLOT_UNIT", "PGSD_B200_SLOT_LAYOUT", "PGSD_B200_SLOT_CSTRIDE", "PGSD_B200_SLOT_DEBUG", "PGSD_B200_SLOT", "PGSD_B200_SLOT_BITS", "PGSD_B200_SLOT_TILE", "PGSD_B200_SLOT_BULK"]
+KNOBS = ["PGSD_B200_SLOT_UNIT", "PGSD_B200_SLOT_LAYOUT", "PGSD_B200_SLOT_CSTRIDE", "PGSD_B200_SLOT", "PGSD_B200_SLOT_BITS",
+         "PGSD_B200_SLOT_TILE", "PGSD_B200_SLOT_BULK", "PGSD_B200_CLUSTER", "PGSD_B200_CLUSTER_TILE", "PGSD_B200_CLUSTER_THREADS",
+         "PGSD_B200_CLUSTER_AGG", "PGSD_B200_CLUSTER_BITS"]
 VARIANTS = [
     ("general path", {"PGSD_B200_SLOT": "0"}),
-    ("slot default", {}),
-    ("slot tile 512", {"PGSD_B200_SLOT_TILE": "512"}),
-    ("slot tile 2048", {"PGSD_B200_SLOT_TILE": "2048"}),
-    ("slot bits 11", {"PGSD_B200_SLOT_BITS": "11"}),
-    ("slot bits 12", {"PGSD_B200_SLOT_BITS": "12"}),
-    ("slot unit 256", {"PGSD_B200_SLOT_UNIT": "8"}),
-    ("slot unit 512", {"PGSD_B200_SLOT_UNIT": "9"}),
-    ("slot unit 1024", {"PGSD_B200_SLOT_UNIT": "10"}),
-    ("slot unit 2048", {"PGSD_B200_SLOT_UNIT": "11"}),
-    ("slot unit 4096", {"PGSD_B200_SLOT_UNIT": "12"}),
-    ("slot flat", {"PGSD_B200_SLOT_LAYOUT": "flat"}),
-    ("slot flat plain loads", {"PGSD_B200_SLOT_LAYOUT": "flat", "PGSD_B200_SLOT_BULK": "0"}),
-    ("slot flat cstride 1", {"PGSD_B200_SLOT_LAYOUT": "flat", "PGSD_B200_SLOT_CSTRIDE": "1"}),
-    # timing experiments (wrong results): what each part of the scatter costs, flat layout
-    ("dbg4 staging only", {"PGSD_B200_SLOT_LAYOUT": "flat", "PGSD_B200_SLOT_DEBUG": "4"}),
-    ("dbg3 staging + atomics", {"PGSD_B200_SLOT_LAYOUT": "flat", "PGSD_B200_SLOT_DEBUG": "3"}),
-    ("dbg1 staging + records at identity positions", {"PGSD_B200_SLOT_LAYOUT": "flat", "PGSD_B200_SLOT_DEBUG": "1"}),
-    ("dbg2 staging + atomics + records at identity positions", {"PGSD_B200_SLOT_LAYOUT": "flat", "PGSD_B200_SLOT_DEBUG": "2"}),
+    ("slot path", {"PGSD_B200_CLUSTER": "0"}),
+    ("cluster default", {}),
+    ("cluster t4096/512", {"PGSD_B200_CLUSTER_TILE": "4096", "PGSD_B200_CLUSTER_THREADS": "512"}),
+    ("cluster t2048/512", {"PGSD_B200_CLUSTER_TILE": "2048", "PGSD_B200_CLUSTER_THREADS": "512"}),
+    ("cluster t2048/256", {"PGSD_B200_CLUSTER_TILE": "2048", "PGSD_B200_CLUSTER_THREADS": "256"}),
+    ("cluster t1024/256", {"PGSD_B200_CLUSTER_TILE": "1024"}),
+    ("cluster no-agg", {"PGSD_B200_CLUSTER_AGG": "0"}),
+    ("cluster plain loads", {"PGSD_B200_SLOT_BULK": "0"}),
+    ("cluster bits 11", {"PGSD_B200_CLUSTER_BITS": "11"}),
+    ("cluster bits 11 t2048", {"PGSD_B200_CLUSTER_BITS": "11", "PGSD_B200_CLUSTER_TILE": "2048"}),
 ]
 if os.environ.get("TIME_SLOT_ONLY"):
     VARIANTS = [v for v in VARIANTS if any(w in v[0] for w in os.environ["TIME_SLOT_ONLY"].split(","))]
@@ -66,7 +60,7 @@ for n in sizes:
                 if best is None or sum(ph) < sum(best):
                     best = ph
             lib.pgsd_b200_reorder_profiling(0)
-            ok = "PGSD_B200_SLOT_DEBUG" in env or np.array_equal(d_sorted.to_numpy(), np.arange(n, dtype=np.uint32)) and \
+            ok = np.array_equal(d_sorted.to_numpy(), np.arange(n, dtype=np.uint32)) and \
                 np.array_equal(d_out[2].to_numpy().view(np.uint32), np.arange(n, dtype=np.uint32))
             print(f"n={n} perm={int(want_perm)} {name:18s}: census {best[0]:.3f} scatter/bucket {best[1]:.3f} pairs {best[2]:.3f} "
                   f"place/gather {best[3]:.3f} = {sum(best):.3f} ms; call {tot:.3f} ms -> {n/tot/1e3:.0f} Mparticles/s, "
