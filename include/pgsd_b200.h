@@ -191,6 +191,9 @@ struct pgsd_b200_stats
     uint64_t file_bytes_read;
     uint64_t collectives; /* all-gathers issued through the communicator */
     double commit_wait_s; /* host time blocked in frame commits (D2H + pwrite drain) */
+    double d2h_busy_s;    /* sum over staged pieces of their D2H copy time (CUDA events on the copy streams) */
+    double file_busy_s;   /* sum over staged pieces of the writer thread's time inside the file write */
+    uint64_t pieces;      /* staged pieces (16 MiB each unless configured otherwise) */
     };
 int pgsd_b200_get_stats(struct pgsd_b200_stats* out);
 int pgsd_b200_reset_stats(void);
@@ -222,6 +225,13 @@ int pgsd_b200_reorder_profiling(int on);
 int pgsd_b200_pack_profiling(int on);
 int pgsd_b200_pack_last_ms(float* ms);
 int pgsd_b200_reorder_phase_ms(float* out4);
+/* K3 file stage without the device (file_stage.cpp), for tests and for measuring the host-side ceiling:
+   pgsd_b200_file_stage_write puts one piece into fd the way a writer thread does (mode 0: auto = mappings on
+   tmpfs, pwrite elsewhere; 1: pwrite; 2: mappings); pgsd_b200_file_stage_ceiling writes `bytes` bytes of host
+   memory at [off, off + bytes) of `path` with the library's own piece size / thread counts / mode and returns the
+   seconds it took (bench.py reports file_ceiling_GBps from it, on the same target as the timed frames). */
+int pgsd_b200_file_stage_write(int fd, const void* buf, uint64_t off, uint64_t len, int mode);
+int pgsd_b200_file_stage_ceiling(const char* path, uint64_t off, uint64_t bytes, double* seconds, int* threads_used, int* mapped);
 /* Device self-tests of failure paths that valid inputs never reach.  which = 0: a kernel waits on an mbarrier
    whose bulk copy never arrives; returns 0 when the bounded wait gave up and reported it (the reorder kernels'
    "a bulk copy did not complete" path), > 0 otherwise. */

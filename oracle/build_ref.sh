@@ -20,8 +20,20 @@ gcc -o "$OUT/ref_driver" "$OUT/ref_driver.o" "$OUT/pgsd_ref.o" "$OUT/mpishim.o" 
 gcc -shared -o "$OUT/libpgsd_ref.so" "$OUT/pgsd_ref.o" "$OUT/mpishim.o" -lpthread
 # the reference's own C++ benchmark (published numbers: CHANGELOG.md:172-194), unmodified
 SCRIPTS="${PGSD_REFERENCE_ROOT:-/root/reference}/pgsd/scripts"
-if [ -f "$SCRIPTS/benchmark-write.cc" ]; then
-    g++ -O2 -w -I"$HERE/shim" -I"$REF" -o "$OUT/benchmark-write" "$SCRIPTS/benchmark-write.cc" \
-        "$OUT/pgsd_ref.o" "$OUT/mpishim.o" -lpthread
-fi
+for b in benchmark-write benchmark-read; do
+    if [ -f "$SCRIPTS/$b.cc" ]; then
+        g++ -O2 -w -I"$HERE/shim" -I"$REF" -o "$OUT/$b" "$SCRIPTS/$b.cc" "$OUT/pgsd_ref.o" "$OUT/mpishim.o" -lpthread
+    fi
+done
+# The reference's pure-Python reader (pypgsd.py + hoomd.py import with numpy only once `mpi4py` resolves to a stub:
+# the MPI name is only used in commented-out code, hoomd.py:574-632).  Staged UNMODIFIED into the git-ignored
+# oracle/_ref/pyref/ so that bench.py's --impl reference read leg times the reference's own decode on the GPU box,
+# where /root/reference does not exist.  Not imported by anything under pgsd_sph_b200/.
+PYREF="$OUT/pyref"
+rm -rf "$PYREF"
+mkdir -p "$PYREF/pgsd" "$PYREF/mpi4py"
+for f in __init__.py version.py pypgsd.py hoomd.py; do
+    cp "$REF/$f" "$PYREF/pgsd/$f"
+done
+printf 'class MPI:\n    pass\n' > "$PYREF/mpi4py/__init__.py"
 echo "built $OUT/ref_driver and $OUT/libpgsd_ref.so from $REF/pgsd.c"

@@ -341,7 +341,7 @@ static int run_script(const char* ops_path, const char* blob_path, const char* o
 /* bench mode: the HOOMD-schema frame of SURVEY.md section 8(d) written `frames` times.
    Input blob = SoA f32/u32 arrays of length N in the order
    pos_x pos_y pos_z vel_x vel_y vel_z density pressure typeid id. */
-static int run_bench(const char* path, uint64_t N, int frames, const char* blob_path, int do_fsync)
+static int run_bench(const char* path, uint64_t N, int frames, const char* blob_path, int do_fsync, int nlogs)
     {
     size_t blob_len = 0;
     const unsigned char* blob = map_blob(blob_path, &blob_len);
@@ -403,6 +403,13 @@ static int run_bench(const char* path, uint64_t N, int frames, const char* blob_
         pgsd_write_chunk(&h, "particles/density", PGSD_TYPE_FLOAT, n, 1, N, 1, start, N, true, 0, soa[6] + start);
         pgsd_write_chunk(&h, "particles/pressure", PGSD_TYPE_FLOAT, n, 1, N, 1, start, N, true, 0, soa[7] + start);
         pgsd_write_chunk(&h, "log/particles/id", PGSD_TYPE_UINT32, n, 1, N, 1, start, N, true, 0, id_g + start);
+        for (int k = 0; k < nlogs; k++) /* BASELINE config 5: per-frame log scalars, root-owned, buffered */
+            {
+            char nm[64];
+            snprintf(nm, sizeof(nm), "log/value/v%d", k);
+            float v = (float)k;
+            pgsd_write_chunk(&h, nm, PGSD_TYPE_FLOAT, 1, 1, 1, 1, 0, 0, false, 0, &v);
+            }
         pgsd_end_frame(&h);
         if (do_fsync)
             {
@@ -432,7 +439,7 @@ int main(int argc, char** argv)
     {
     if (argc < 2)
         {
-        fprintf(stderr, "usage: ref_driver script <ops> <blob> <out_prefix> | bench <file> <N> <frames> <blob> [fsync]\n");
+        fprintf(stderr, "usage: ref_driver script <ops> <blob> <out_prefix> | bench <file> <N> <frames> <blob> [fsync|nofsync [n_log_scalars]]\n");
         return 2;
         }
     MPI_Init(NULL, NULL);
@@ -443,7 +450,7 @@ int main(int argc, char** argv)
         rc = run_script(argv[2], argv[3], argv[4]);
     else if (!strcmp(argv[1], "bench") && argc >= 6)
         rc = run_bench(argv[2], strtoull(argv[3], NULL, 10), atoi(argv[4]), argv[5],
-                       argc >= 7 && !strcmp(argv[6], "fsync"));
+                       argc >= 7 && !strcmp(argv[6], "fsync"), argc >= 8 ? atoi(argv[7]) : 0);
     MPI_Finalize();
     return rc;
     }

@@ -121,7 +121,8 @@ class Field(C.Structure):  # struct pgsd_b200_field
 class Stats(C.Structure):  # struct pgsd_b200_stats
     _fields_ = [("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("file_bytes_written", C.c_uint64), ("file_bytes_read", C.c_uint64),
-                ("collectives", C.c_uint64), ("commit_wait_s", C.c_double)]
+                ("collectives", C.c_uint64), ("commit_wait_s", C.c_double), ("d2h_busy_s", C.c_double),
+                ("file_busy_s", C.c_double), ("pieces", C.c_uint64)]
 
 
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_size_t)
@@ -199,6 +200,8 @@ SIGNATURES = {
     "pgsd_b200_reorder_profiling": (_i, [_i]),
     "pgsd_b200_reorder_phase_ms": (_i, [C.POINTER(C.c_float)]),
     "pgsd_b200_selftest": (_i, [_i]),
+    "pgsd_b200_file_stage_write": (_i, [_i, _vp, _u64, _u64, _i]),
+    "pgsd_b200_file_stage_ceiling": (_i, [C.c_char_p, _u64, _u64, C.POINTER(C.c_double), C.POINTER(_i), C.POINTER(_i)]),
 }
 
 _lib = None

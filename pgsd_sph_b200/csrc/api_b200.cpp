@@ -4,6 +4,10 @@
 #include "../../include/pgsd_b200.h"
 #include "comm.h"
 #include "device.h"
+#include "file_stage.h"
+
+#include <fcntl.h>
+#include <unistd.h>
 #include "file_internal.h"
 
 #include <cstring>
@@ -11,6 +15,14 @@
 #include <vector>
 
 using namespace pgsdb;
+
+static int replace_comm(Comm* c)
+    {
+    if (comm_replace(c))
+        return PGSD_SUCCESS;
+    set_last_error("the communicator cannot be replaced while files opened under it are still open");
+    return PGSD_ERROR_INVALID_ARGUMENT;
+    }
 
 extern "C" {
 
@@ -22,8 +34,7 @@ int pgsd_b200_comm_init_host(int rank, int nprocs, pgsd_b200_allgather_fn fn, vo
         set_last_error("comm_init_host: bad rank/nprocs or missing all-gather callback");
         return PGSD_ERROR_INVALID_ARGUMENT;
         }
-    comm_replace(nprocs == 1 ? nullptr : make_host_comm(rank, nprocs, fn, ctx));
-    return PGSD_SUCCESS;
+    return replace_comm(nprocs == 1 ? nullptr : make_host_comm(rank, nprocs, fn, ctx));
     }
 
 int pgsd_b200_comm_init_shm(int rank, int nprocs, const char* segment_name)
@@ -34,10 +45,7 @@ int pgsd_b200_comm_init_shm(int rank, int nprocs, const char* segment_name)
         return PGSD_ERROR_INVALID_ARGUMENT;
         }
     if (nprocs == 1)
-        {
-        comm_replace(nullptr);
-        return PGSD_SUCCESS;
-        }
+        return replace_comm(nullptr);
     std::string err;
     Comm* c = make_shm_comm(rank, nprocs, segment_name, err);
     if (!c)
@@ -45,8 +53,7 @@ int pgsd_b200_comm_init_shm(int rank, int nprocs, const char* segment_name)
         set_last_error(err);
         return PGSD_ERROR_IO;
         }
-    comm_replace(c);
-    return PGSD_SUCCESS;
+    return replace_comm(c);
     }
 
 int pgsd_b200_nccl_unique_id(void* out128)
@@ -76,15 +83,10 @@ int pgsd_b200_comm_init_nccl(int rank, int nprocs, const void* unique_id128, int
         set_last_error(err);
         return PGSD_ERROR_IO;
         }
-    comm_replace(c);
-    return PGSD_SUCCESS;
+    return replace_comm(c);
     }
 
-int pgsd_b200_comm_finalize(void)
-    {
-    comm_replace(nullptr);
-    return PGSD_SUCCESS;
-    }
+int pgsd_b200_comm_finalize(void) { return replace_comm(nullptr); }
 
 int pgsd_b200_comm_rank(void) { return comm()->rank; }
 int pgsd_b200_comm_size(void) { return comm()->nprocs; }
@@ -316,6 +318,9 @@ int pgsd_b200_get_stats(struct pgsd_b200_stats* out)
     out->file_bytes_read = s.file_bytes_read;
     out->collectives = g_collectives;
     out->commit_wait_s = s.commit_wait_s;
+    out->d2h_busy_s = s.d2h_busy_s;
+    out->file_busy_s = s.file_busy_s;
+    out->pieces = s.pieces;
     return PGSD_SUCCESS;
     }
 
@@ -357,6 +362,35 @@ int pgsd_b200_reorder_profiling(int on)
     return 0;
     }
 int pgsd_b200_reorder_phase_ms(float* out4) { return out4 ? dev_reorder_phase_ms(out4) : PGSD_ERROR_INVALID_ARGUMENT; }
+int pgsd_b200_file_stage_write(int fd, const void* buf, uint64_t off, uint64_t len, int mode)
+    {
+    if (fd < 0 || (len > 0 && buf == nullptr) || mode < 0 || mode > 2)
+        return PGSD_ERROR_INVALID_ARGUMENT;
+    const bool use_mmap = mode == 2 || (mode == 0 && file_is_tmpfs(fd));
+    uint64_t left = 0;
+    return file_write_piece(fd, (const char*)buf, off, len, use_mmap, &left) ? PGSD_SUCCESS : PGSD_ERROR_IO;
+    }
+
+int pgsd_b200_file_stage_ceiling(const char* path, uint64_t off, uint64_t bytes, double* seconds, int* threads_used, int* mapped)
+    {
+    if (path == nullptr || seconds == nullptr)
+        return PGSD_ERROR_INVALID_ARGUMENT;
+    const int fd = open(path, O_RDWR | O_CREAT, 0644);
+    if (fd < 0)
+        return PGSD_ERROR_IO;
+    int writers = 8, pw = 2, mode = 0;
+    dev_file_stage_config(&writers, &pw, &mode);
+    const bool use_mmap = mode == 2 || (mode == 0 && file_is_tmpfs(fd));
+    const int threads = use_mmap ? writers : (pw < writers ? pw : writers);
+    *seconds = file_stage_ceiling(fd, off, bytes, dev_slot_bytes(), threads, use_mmap);
+    if (threads_used)
+        *threads_used = threads;
+    if (mapped)
+        *mapped = use_mmap ? 1 : 0;
+    close(fd);
+    return *seconds < 0 ? PGSD_ERROR_IO : PGSD_SUCCESS;
+    }
+
 int pgsd_b200_selftest(int which)
     {
     if (which == 0)

@@ -139,11 +139,28 @@ Comm* g_comm = &g_single;
 
 Comm* comm() { return g_comm; }
 
-void comm_replace(Comm* c)
+static int g_comm_users = 0; // open file handles that hold a pointer to the communicator
+void comm_acquire() { g_comm_users++; }
+void comm_release()
     {
+    if (g_comm_users > 0)
+        g_comm_users--;
+    }
+int comm_users() { return g_comm_users; }
+
+bool comm_replace(Comm* c)
+    {
+    if (g_comm_users > 0)
+        {
+        // open files keep a pointer to the communicator they were opened under
+        if (c != nullptr && c != &g_single)
+            delete c;
+        return false;
+        }
     if (g_comm != &g_single)
         delete g_comm;
     g_comm = c ? c : &g_single;
+    return true;
     }
 
 const char* comm_kind_name()

@@ -45,7 +45,12 @@ class Comm
 void scan_sizes_host(const uint64_t* gathered, int P, size_t n, int rank, SizeScan* out);
 
 Comm* comm();                 // never NULL (Single by default)
-void comm_replace(Comm* c);   // takes ownership; NULL -> back to Single
+// Takes ownership; NULL -> back to Single.  Refused (false, `c` deleted) while file handles opened under the current
+// communicator are still open: they keep a pointer to it.
+bool comm_replace(Comm* c);
+void comm_acquire(); // a file handle starts / stops using comm()
+void comm_release();
+int comm_users();
 const char* comm_kind_name();
 
 Comm* make_host_comm(int rank, int nprocs,

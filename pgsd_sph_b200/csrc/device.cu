@@ -8,6 +8,7 @@
 // K2 replaces MPI_Allgather + prefix loop + MPI_Allreduce SUM/MAX (pgsd.c:1126,1150-1152,
 // 1162,2157,2242): one ncclAllGather of the frame's u64 size vector + a device scan.
 #include "device_internal.h"
+#include "file_stage.h"
 
 #include <nccl.h> // types only; the library is dlopen()ed so that CPU-only hosts can load us
 
@@ -24,6 +25,7 @@
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <sys/statvfs.h>
+#include <sys/uio.h>
 #include <unistd.h>
 #include <vector>
 
@@ -69,13 +71,36 @@ struct ArenaFrame
     std::vector<Block> blocks;
     std::atomic<long> outstanding { 0 }; // pinned-slot writes not yet finished
     cudaEvent_t packed = nullptr;        // recorded on the user stream after the frame's K1 launches
-    bool assembling = false;
+    cudaEvent_t k1[2] = { nullptr, nullptr }; // trace: around the frame's last K1 launch
+    bool k1_timed = false;
+    bool assembling = false;             // owned by one writable file handle until it is submitted or abandoned
+    uint64_t seq = 0;                    // submit order (trace)
     };
 
 struct Slot
     {
     char* host = nullptr;
-    cudaEvent_t copied = nullptr;
+    cudaEvent_t t0 = nullptr; // recorded on the copy stream before the piece's D2H copy ...
+    cudaEvent_t t1 = nullptr; // ... and after it (the writer thread waits on this one)
+    };
+
+// PGSD_B200_TRACE=<file>: every K1 launch, D2H piece and file piece with its interval on one clock (host
+// steady_clock; device intervals are placed through a calibrated base event), written as a Chrome trace at
+// shutdown.  Evidence for the K1(k+1) || D2H(k) || file(k-1) overlap; off by default.
+struct TraceEvent
+    {
+    char kind; // 'K' K1, 'D' D2H piece, 'F' file piece
+    uint64_t frame;
+    double t0_us, t1_us;
+    uint64_t bytes;
+    int lane; // stream / writer thread
+    };
+
+struct Seg // one chunk inside a bundled copy
+    {
+    uint64_t dev_off; // from the bundle's first byte
+    uint64_t bytes;
+    uint64_t file_off;
     };
 
 struct StageJob
@@ -85,6 +110,10 @@ struct StageJob
     uint64_t bytes;
     uint64_t file_off;
     ArenaFrame* frame;
+    // Small frames (BASELINE config 5: 4096 particles, 6 device chunks of 16-48 KB): the chunks of a frame are
+    // neighbours in the arena, so ONE D2H copy of their span replaces one copy + two event records + a slot per chunk,
+    // and the writer thread puts them into the file with pwritev (file-contiguous runs in one call).
+    std::vector<Seg> segs;
     };
 
 struct WriteItem
@@ -94,6 +123,8 @@ struct WriteItem
     uint64_t file_off;
     uint64_t bytes;
     ArenaFrame* frame;
+    int stream; // copy stream the piece was staged on (trace)
+    std::vector<Seg> segs;
     };
 
 struct Ctx
@@ -110,8 +141,20 @@ struct Ctx
     uint32_t n_slots = 8;
     uint64_t slot_bytes = 16ull << 20;
     uint32_t n_writers = 8;
-    bool file_mmap = true; // PGSD_B200_FILE_MODE=pwrite switches the writer threads to pwrite()
-    uint32_t max_frames = 3;
+    FileMode file_mode = FileMode::Auto; // PGSD_B200_FILE_MODE: auto (mappings on tmpfs only) | pwrite | mmap
+    uint32_t pwrite_threads = 2; // pwrite-mode pieces in flight: buffered writes to one file serialise on the inode
+                                 // lock, more threads only add contention (ext4: 6.7 GB/s at 1-2, 5.2 at 8-16)
+    uint32_t pwrite_active = 0;
+    std::condition_variable cv_pwrite;
+    uint32_t max_frames = 3;     // frames in flight (packed, not yet in the file)
+    uint64_t frame_seq = 0;
+
+    // trace
+    bool trace_on = false;
+    std::string trace_path;
+    std::vector<TraceEvent> trace;
+    cudaEvent_t trace_base = nullptr;
+    std::chrono::steady_clock::time_point trace_t0;
 
     std::vector<Slot> slots;
     std::vector<int> free_slots;
@@ -127,8 +170,6 @@ struct Ctx
     std::atomic<bool> io_error { false };
 
     std::vector<ArenaFrame*> frames;
-    ArenaFrame* cur = nullptr;
-
 
     // reorder_host scratch
     char* scratch = nullptr;
@@ -136,62 +177,49 @@ struct Ctx
     };
 Ctx g;
 
-// One pinned piece -> file.  Buffered pwrite()s to one file serialise on the inode lock whatever
-// the thread count (measured: 3.6 GB/s on tmpfs for 1..16 threads, profiles/r1_pwrite_sweep.txt),
-// so by default a piece is copied through a short-lived shared mapping of its file range instead:
-// page-cache inserts then run in parallel on all writer threads (8.5 GB/s on the same box).  The
-// file is extended first with a 1-byte fallocate at the piece's end, which never shrinks a file
-// another rank has already extended further.  Anything the mapping path cannot do (fallocate or
-// mmap unsupported) falls back to pwrite for that piece.
-bool write_piece(int fd, const char* p, uint64_t off, uint64_t len, uint64_t* left_out)
+double trace_now_us()
     {
-    uint64_t left = len;
-    // small pieces stay on pwrite: they share pages with other writers' pieces and gain nothing
-    if (g.file_mmap && len >= (1u << 20))
+    return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - g.trace_t0).count();
+    }
+// device interval [e0, e1] on the host clock (both events have completed)
+bool trace_device_interval(cudaEvent_t e0, cudaEvent_t e1, double* t0_us, double* t1_us)
+    {
+    float a = 0.f, b = 0.f;
+    if (cudaEventElapsedTime(&a, g.trace_base, e0) != cudaSuccess || cudaEventElapsedTime(&b, g.trace_base, e1) != cudaSuccess)
         {
-        static const uint64_t page = (uint64_t)sysconf(_SC_PAGESIZE);
-        struct stat st;
-        bool sized = fstat(fd, &st) == 0 && S_ISREG(st.st_mode);
-        // a store into a mapping cannot report ENOSPC (it raises SIGBUS): leave nearly full file
-        // systems to pwrite, which returns the error
-        struct statvfs vfs;
-        if (sized && (fstatvfs(fd, &vfs) != 0 || (uint64_t)vfs.f_bavail * vfs.f_frsize < 4 * len + (256ull << 20)))
-            sized = false;
-        if (sized && (uint64_t)st.st_size < off + len)
-            sized = fallocate(fd, 0, (off_t)(off + len - 1), 1) == 0;
-        if (sized)
-            {
-            const uint64_t a = off & ~(page - 1);
-            const size_t maplen = (size_t)(off - a + len);
-            void* m = mmap(nullptr, maplen, PROT_READ | PROT_WRITE, MAP_SHARED, fd, (off_t)a);
-            if (m != MAP_FAILED)
-                {
-                memcpy((char*)m + (off - a), p, len);
-                munmap(m, maplen);
-                *left_out = 0;
-                return true;
-                }
-            }
+        cudaGetLastError();
+        return false;
         }
-    while (left > 0)
-        {
-        ssize_t k = pwrite(fd, p, left, (off_t)off);
-        if (k < 0)
-            {
-            if (errno == EINTR)
-                continue;
-            *left_out = left;
-            return false;
-            }
-        p += k;
-        off += (uint64_t)k;
-        left -= (uint64_t)k;
-        }
-    *left_out = 0;
+    *t0_us = 1e3 * a;
+    *t1_us = 1e3 * b;
     return true;
     }
+void trace_dump()
+    {
+    if (!g.trace_on || g.trace_path.empty())
+        return;
+    FILE* f = fopen(g.trace_path.c_str(), "w");
+    if (!f)
+        return;
+    fprintf(f, "{\"traceEvents\":[\n");
+    bool first = true;
+    for (const TraceEvent& e : g.trace)
+        {
+        const char* name = e.kind == 'K' ? "K1 pack" : e.kind == 'D' ? "D2H piece" : "file piece";
+        const int tid = e.kind == 'K' ? 0 : e.kind == 'D' ? 10 + e.lane : 100 + e.lane;
+        fprintf(f, "%s{\"name\":\"%s f%llu\",\"cat\":\"%c\",\"ph\":\"X\",\"pid\":%d,\"tid\":%d,\"ts\":%.1f,\"dur\":%.1f,"
+                   "\"args\":{\"frame\":%llu,\"bytes\":%llu}}",
+                first ? "" : ",\n", name, (unsigned long long)e.frame, e.kind, g.device, tid, e.t0_us, e.t1_us - e.t0_us,
+                (unsigned long long)e.frame, (unsigned long long)e.bytes);
+        first = false;
+        }
+    fprintf(f, "\n]}\n");
+    fclose(f);
+    g.trace.clear();
+    }
 
-void writer_main()
+// One pinned piece -> file: see file_stage.cpp for the two ways and why.
+void writer_main(int widx)
     {
     cudaSetDevice(g.device);
     for (;;)
@@ -202,21 +230,98 @@ void writer_main()
             g.cv_write.wait(lk, [] { return g.stop || !g.write_q.empty(); });
             if (g.write_q.empty())
                 return;
-            it = g.write_q.front();
+            it = std::move(g.write_q.front());
             g.write_q.pop_front();
             }
-        bool ok = cudaEventSynchronize(g.slots[it.slot].copied) == cudaSuccess;
+        Slot& sl = g.slots[it.slot];
+        bool ok = cudaEventSynchronize(sl.t1) == cudaSuccess;
+        float d2h_ms = 0.f;
+        if (ok && cudaEventElapsedTime(&d2h_ms, sl.t0, sl.t1) != cudaSuccess)
+            {
+            cudaGetLastError();
+            d2h_ms = 0.f;
+            }
+        double dt0 = 0, dt1 = 0;
+        const bool traced = g.trace_on && ok && trace_device_interval(sl.t0, sl.t1, &dt0, &dt1);
         uint64_t left = it.bytes;
+        double busy = 0, ft0 = 0, ft1 = 0;
         if (ok)
-            ok = write_piece(it.fd, g.slots[it.slot].host, it.file_off, it.bytes, &left);
+            {
+            const bool use_mmap = g.file_mode == FileMode::Mmap || (g.file_mode == FileMode::Auto && file_is_tmpfs(it.fd));
+            if (!use_mmap)
+                {
+                std::unique_lock<std::mutex> lk(g.mu);
+                g.cv_pwrite.wait(lk, [] { return g.pwrite_active < g.pwrite_threads; });
+                g.pwrite_active++;
+                }
+            const auto t0 = std::chrono::steady_clock::now();
+            if (g.trace_on)
+                ft0 = trace_now_us();
+            if (it.segs.empty())
+                ok = file_write_piece(it.fd, sl.host, it.file_off, it.bytes, use_mmap, &left);
+            else
+                {
+                // bundled small chunks: file-contiguous runs leave with one pwritev each
+                left = 0;
+                size_t i = 0;
+                while (ok && i < it.segs.size())
+                    {
+                    struct iovec iov[16];
+                    int k = 0;
+                    uint64_t run = 0;
+                    const uint64_t at = it.segs[i].file_off;
+                    while (i < it.segs.size() && k < 16 && it.segs[i].file_off == at + run)
+                        {
+                        iov[k].iov_base = sl.host + it.segs[i].dev_off;
+                        iov[k].iov_len = (size_t)it.segs[i].bytes;
+                        run += it.segs[i].bytes;
+                        k++;
+                        i++;
+                        }
+                    const ssize_t w = pwritev(it.fd, iov, k, (off_t)at);
+                    if (w != (ssize_t)run)
+                        {
+                        // short or failed vector write: the plain path finishes (or reports) every segment
+                        for (int q = 0; q < k && ok; q++)
+                            {
+                            uint64_t l2 = 0;
+                            uint64_t o = at;
+                            for (int r = 0; r < q; r++)
+                                o += iov[r].iov_len;
+                            ok = file_write_piece(it.fd, (const char*)iov[q].iov_base, o, iov[q].iov_len, false, &l2);
+                            left += l2;
+                            }
+                        }
+                    }
+                }
+            if (g.trace_on)
+                ft1 = trace_now_us();
+            busy = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            if (!use_mmap)
+                {
+                    {
+                    std::lock_guard<std::mutex> lk(g.mu);
+                    g.pwrite_active--;
+                    }
+                g.cv_pwrite.notify_one();
+                }
+            }
         if (!ok)
             g.io_error = true;
             {
             std::lock_guard<std::mutex> lk(g.mu);
             g.free_slots.push_back(it.slot);
+            g_stats.file_bytes_written += it.bytes - left;
+            g_stats.file_busy_s += busy;
+            g_stats.d2h_busy_s += 1e-3 * d2h_ms;
+            g_stats.pieces++;
+            if (traced)
+                {
+                g.trace.push_back(TraceEvent { 'D', it.frame->seq, dt0, dt1, it.bytes, it.stream });
+                g.trace.push_back(TraceEvent { 'F', it.frame->seq, ft0, ft1, it.bytes, widx });
+                }
             it.frame->outstanding--;
             g.jobs_outstanding--;
-            g_stats.file_bytes_written += it.bytes - left;
             }
         g.cv_slot.notify_one();
         g.cv_done.notify_all();
@@ -235,13 +340,12 @@ void stager_main()
             g.cv_stage.wait(lk, [] { return g.stop || !g.stage_q.empty(); });
             if (g.stage_q.empty())
                 return;
-            job = g.stage_q.front();
+            job = std::move(g.stage_q.front());
             g.stage_q.pop_front();
             }
         uint64_t done = 0;
-        while (done < job.bytes)
+        if (!job.segs.empty())
             {
-            uint64_t len = job.bytes - done < g.slot_bytes ? job.bytes - done : g.slot_bytes;
             int slot;
                 {
                 std::unique_lock<std::mutex> lk(g.mu);
@@ -251,17 +355,54 @@ void stager_main()
                 g.jobs_outstanding++;
                 job.frame->outstanding++;
                 }
-            cudaStream_t st = g.copy[rr++ & 1];
+            const int si = (int)(rr++ & 1);
+            cudaStream_t st = g.copy[si];
             bool ok = cudaStreamWaitEvent(st, job.frame->packed, 0) == cudaSuccess
+                      && cudaEventRecord(g.slots[slot].t0, st) == cudaSuccess
+                      && cudaMemcpyAsync(g.slots[slot].host, job.dev, job.bytes, cudaMemcpyDeviceToHost, st) == cudaSuccess
+                      && cudaEventRecord(g.slots[slot].t1, st) == cudaSuccess;
+            if (!ok)
+                g.io_error = true;
+            uint64_t payload = 0;
+            for (const Seg& sg : job.segs)
+                payload += sg.bytes;
+                {
+                std::lock_guard<std::mutex> lk(g.mu);
+                g_stats.d2h_bytes += job.bytes;
+                WriteItem wi { slot, job.fd, 0, payload, job.frame, si, {} };
+                wi.segs.swap(job.segs);
+                g.write_q.push_back(std::move(wi));
+                }
+            g.cv_write.notify_one();
+            done = job.bytes;
+            }
+        while (done < job.bytes)
+            {
+            // interior piece boundaries fall on page boundaries of the FILE (file_stage.cpp: page ownership)
+            uint64_t len = done == 0 ? file_first_piece_len(job.file_off, job.bytes, g.slot_bytes)
+                                     : (job.bytes - done < g.slot_bytes ? job.bytes - done : g.slot_bytes);
+            int slot;
+                {
+                std::unique_lock<std::mutex> lk(g.mu);
+                g.cv_slot.wait(lk, [] { return !g.free_slots.empty(); });
+                slot = g.free_slots.back();
+                g.free_slots.pop_back();
+                g.jobs_outstanding++;
+                job.frame->outstanding++;
+                }
+            const int si = (int)(rr++ & 1);
+            cudaStream_t st = g.copy[si];
+            bool ok = cudaStreamWaitEvent(st, job.frame->packed, 0) == cudaSuccess
+                      && cudaEventRecord(g.slots[slot].t0, st) == cudaSuccess
                       && cudaMemcpyAsync(g.slots[slot].host, job.dev + done, len, cudaMemcpyDeviceToHost, st)
                              == cudaSuccess
-                      && cudaEventRecord(g.slots[slot].copied, st) == cudaSuccess;
+                      && cudaEventRecord(g.slots[slot].t1, st) == cudaSuccess;
             if (!ok)
                 g.io_error = true;
                 {
                 std::lock_guard<std::mutex> lk(g.mu);
                 g_stats.d2h_bytes += len;
-                g.write_q.push_back(WriteItem { slot, job.fd, job.file_off + done, len, job.frame });
+                g.write_q.push_back(WriteItem { slot, job.fd, job.file_off + done, len, job.frame, si, {} });
                 }
             g.cv_write.notify_one();
             done += len;
@@ -285,7 +426,8 @@ int start_threads()
     for (uint32_t i = 0; i < g.n_slots; i++)
         {
         CUDA_TRY(cudaHostAlloc((void**)&g.slots[i].host, g.slot_bytes, cudaHostAllocDefault), -6);
-        CUDA_TRY(cudaEventCreateWithFlags(&g.slots[i].copied, cudaEventDisableTiming), -1);
+        CUDA_TRY(cudaEventCreate(&g.slots[i].t0), -1);
+        CUDA_TRY(cudaEventCreate(&g.slots[i].t1), -1);
         g.free_slots.push_back((int)i);
         }
     g.stop = false;
@@ -294,12 +436,12 @@ int start_threads()
         {
         // joinable std::thread objects must not reach static destruction: finish queued file
         // writes and join at exit (registered after the CUDA runtime came up, so it runs first)
-        atexit([]() { dev_drain(); stop_threads_at_exit(); });
+        atexit([]() { dev_drain(); stop_threads_at_exit(); trace_dump(); });
         exit_hook = true;
         }
     g.stager = std::thread(stager_main);
     for (uint32_t i = 0; i < g.n_writers; i++)
-        g.writers.emplace_back(writer_main);
+        g.writers.emplace_back(writer_main, (int)i);
     g.threads_running = true;
     return 0;
     }
@@ -325,8 +467,10 @@ void stop_threads()
         {
         if (s.host)
             cudaFreeHost(s.host);
-        if (s.copied)
-            cudaEventDestroy(s.copied);
+        if (s.t0)
+            cudaEventDestroy(s.t0);
+        if (s.t1)
+            cudaEventDestroy(s.t1);
         }
     g.slots.clear();
     g.free_slots.clear();
@@ -358,36 +502,43 @@ int arena_alloc(ArenaFrame* f, uint64_t bytes, void** out)
     return 0;
     }
 
-// the frame being assembled; waits for a recycled arena when max_frames are in flight
-int current_frame(ArenaFrame** out)
+// A frame arena for a file handle that starts assembling a frame.  At most max_frames packed frames wait for the
+// file at a time: when that many are in flight the caller waits for the oldest to land (this is the back-pressure
+// of the whole pipeline).  Frames that other handles are still assembling do not count -- they cannot finish by
+// waiting -- so a new arena is created for the caller instead.
+int acquire_frame(ArenaFrame** out)
     {
-    if (g.cur)
-        {
-        *out = g.cur;
-        return 0;
-        }
+    ArenaFrame* got = nullptr;
     std::unique_lock<std::mutex> lk(g.mu);
     for (;;)
         {
+        size_t in_flight = 0;
         for (ArenaFrame* f : g.frames)
-            if (!f->assembling && f->outstanding.load() == 0)
+            {
+            if (f->assembling)
+                continue;
+            if (f->outstanding.load() == 0)
                 {
-                g.cur = f;
+                got = f;
                 break;
                 }
-        if (g.cur)
+            in_flight++;
+            }
+        if (got)
             break;
-        if (g.frames.size() < g.max_frames)
+        if (in_flight < g.max_frames)
             {
             ArenaFrame* f = new ArenaFrame;
-            if (cudaEventCreateWithFlags(&f->packed, cudaEventDisableTiming) != cudaSuccess)
+            if (cudaEventCreateWithFlags(&f->packed, cudaEventDisableTiming) != cudaSuccess
+                || cudaEventCreate(&f->k1[0]) != cudaSuccess || cudaEventCreate(&f->k1[1]) != cudaSuccess)
                 {
                 delete f;
                 set_last_error("cudaEventCreate failed");
+                cudaGetLastError();
                 return -1;
                 }
             g.frames.push_back(f);
-            g.cur = f;
+            got = f;
             break;
             }
         auto t0 = std::chrono::steady_clock::now();
@@ -395,10 +546,11 @@ int current_frame(ArenaFrame** out)
         g_stats.commit_wait_s
             += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         }
-    g.cur->assembling = true;
-    for (auto& b : g.cur->blocks)
-        b.used = 0;
-    *out = g.cur;
+    got->assembling = true;
+    got->k1_timed = false;
+    for (auto& bl : got->blocks)
+        bl.used = 0;
+    *out = got;
     return 0;
     }
     } // namespace
@@ -462,14 +614,35 @@ int dev_init(int device)
     CUDA_TRY(cudaStreamCreateWithFlags(&g.copy[0], cudaStreamNonBlocking), -1);
     CUDA_TRY(cudaStreamCreateWithFlags(&g.copy[1], cudaStreamNonBlocking), -1);
     CUDA_TRY(cudaStreamCreateWithFlags(&g.aux, cudaStreamNonBlocking), -1);
-    if (const char* m = getenv("PGSD_B200_FILE_MODE"))
-        g.file_mmap = strcmp(m, "pwrite") != 0;
+    g.file_mode = file_mode_from_env();
     if (const char* w = getenv("PGSD_B200_WRITER_THREADS"))
         {
         int n = atoi(w);
         if (n >= 1 && n <= 64)
             g.n_writers = (uint32_t)n;
         }
+    if (const char* w = getenv("PGSD_B200_PWRITE_THREADS"))
+        {
+        int n = atoi(w);
+        if (n >= 1 && n <= 64)
+            g.pwrite_threads = (uint32_t)n;
+        }
+    if (const char* t = getenv("PGSD_B200_TRACE"))
+        if (*t)
+            {
+            // device intervals are measured from this event; its completion time is host time 0 of the trace
+            g.trace_path = t;
+            if (g.trace_path.find("%d") != std::string::npos)
+                g.trace_path.replace(g.trace_path.find("%d"), 2, std::to_string(device));
+            if (cudaEventCreate(&g.trace_base) == cudaSuccess && cudaEventRecord(g.trace_base, g.copy[0]) == cudaSuccess
+                && cudaEventSynchronize(g.trace_base) == cudaSuccess)
+                {
+                g.trace_t0 = std::chrono::steady_clock::now();
+                g.trace_on = true;
+                }
+            else
+                cudaGetLastError();
+            }
     g.inited = true;
     return 0;
     }
@@ -486,16 +659,26 @@ void dev_shutdown()
         return;
     dev_drain();
     stop_threads();
+    trace_dump();
+    // an arena a writable handle is still assembling stays alive (its chunks are referenced by that handle)
+    std::vector<ArenaFrame*> keep;
     for (ArenaFrame* f : g.frames)
         {
+        if (f->assembling)
+            {
+            keep.push_back(f);
+            continue;
+            }
         for (auto& b : f->blocks)
             cudaFree(b.ptr);
         if (f->packed)
             cudaEventDestroy(f->packed);
+        for (cudaEvent_t e : f->k1)
+            if (e)
+                cudaEventDestroy(e);
         delete f;
         }
-    g.frames.clear();
-    g.cur = nullptr;
+    g.frames.swap(keep);
     readers_release();
     cache_release_all();
     if (g.scratch)
@@ -526,6 +709,25 @@ bool dev_is_device_pointer(const void* p)
 
 void dev_set_user_stream(void* s) { g.user = (cudaStream_t)s; }
 void* dev_user_stream() { return (void*)g.user; }
+
+void dev_file_stage_config(int* writers, int* pwrite_threads, int* mode)
+    {
+    if (!g.inited)
+        {
+        // same defaults / environment as dev_init, without touching CUDA (host-only tools and tests)
+        g.file_mode = file_mode_from_env();
+        if (const char* w = getenv("PGSD_B200_WRITER_THREADS"))
+            if (atoi(w) >= 1 && atoi(w) <= 64)
+                g.n_writers = (uint32_t)atoi(w);
+        if (const char* w = getenv("PGSD_B200_PWRITE_THREADS"))
+            if (atoi(w) >= 1 && atoi(w) <= 64)
+                g.pwrite_threads = (uint32_t)atoi(w);
+        }
+    *writers = (int)g.n_writers;
+    *pwrite_threads = (int)g.pwrite_threads;
+    *mode = (int)g.file_mode;
+    }
+uint64_t dev_slot_bytes() { return g.slot_bytes; }
 
 int dev_configure_staging(uint32_t n_slots, uint64_t slot_bytes, uint32_t writer_threads)
     {
@@ -605,15 +807,21 @@ int dev_pack_last_ms(float* ms)
     return 0;
     }
 
-int dev_arena_pack(PackRequest* reqs, int n)
+int dev_arena_pack(PackRequest* reqs, int n, void** frame_io)
     {
     int rc = dev_init(-1);
     if (rc != 0)
         return rc;
-    ArenaFrame* f = nullptr;
-    rc = current_frame(&f);
-    if (rc != 0)
-        return rc;
+    if (frame_io == nullptr)
+        return -2;
+    ArenaFrame* f = (ArenaFrame*)*frame_io;
+    if (f == nullptr)
+        {
+        rc = acquire_frame(&f);
+        if (rc != 0)
+            return rc;
+        *frame_io = f;
+        }
     bool need_sync = false;
     int i0 = 0;
     while (i0 < n)
@@ -678,9 +886,16 @@ int dev_arena_pack(PackRequest* reqs, int n)
                 }
             cudaEventRecord(g_pack_ev[0], g.user);
             }
+        if (g.trace_on)
+            cudaEventRecord(f->k1[0], g.user);
         rc = pack_launch(segs, ns, g.user);
         if (rc != 0)
             return rc;
+        if (g.trace_on)
+            {
+            cudaEventRecord(f->k1[1], g.user);
+            f->k1_timed = true;
+            }
         if (g_pack_prof)
             {
             cudaEventRecord(g_pack_ev[1], g.user);
@@ -697,9 +912,10 @@ int dev_arena_pack(PackRequest* reqs, int n)
     }
 
 // ------------------------------------------------------------------------------ K3
-int dev_frame_submit(int fd, const WriteJob* jobs, int njobs)
+int dev_frame_submit(int fd, const WriteJob* jobs, int njobs, void* frame)
     {
-    if (!g.inited || g.cur == nullptr)
+    ArenaFrame* f = (ArenaFrame*)frame;
+    if (!g.inited || f == nullptr)
         {
         if (njobs == 0)
             return 0;
@@ -709,23 +925,70 @@ int dev_frame_submit(int fd, const WriteJob* jobs, int njobs)
     int rc = start_threads();
     if (rc != 0)
         return rc;
-    ArenaFrame* f = g.cur;
     CUDA_TRY(cudaEventRecord(f->packed, g.user), -1);
+    if (g.trace_on && f->k1_timed)
+        {
+        double t0 = 0, t1 = 0;
+        if (cudaEventSynchronize(f->k1[1]) == cudaSuccess && trace_device_interval(f->k1[0], f->k1[1], &t0, &t1))
+            {
+            std::lock_guard<std::mutex> lk(g.mu);
+            g.trace.push_back(TraceEvent { 'K', g.frame_seq, t0, t1, 0, 0 });
+            }
+        }
         {
         std::lock_guard<std::mutex> lk(g.mu);
+        f->seq = g.frame_seq++;
+        // small frame: all chunks inside one short span of the arena -> one bundled copy
+        const char* lo = nullptr;
+        const char* hi = nullptr;
+        int nz = 0;
         for (int i = 0; i < njobs; i++)
             {
             if (jobs[i].bytes == 0)
                 continue;
+            const char* a = (const char*)jobs[i].dev_ptr;
+            lo = (lo == nullptr || a < lo) ? a : lo;
+            hi = (hi == nullptr || a + jobs[i].bytes > hi) ? a + jobs[i].bytes : hi;
+            nz++;
+            }
+        const uint64_t bundle_max = g.slot_bytes < (4ull << 20) ? g.slot_bytes : (4ull << 20);
+        if (nz >= 2 && (uint64_t)(hi - lo) <= bundle_max)
+            {
+            StageJob job { fd, lo, (uint64_t)(hi - lo), 0, f, {} };
+            for (int i = 0; i < njobs; i++)
+                if (jobs[i].bytes)
+                    job.segs.push_back(Seg { (uint64_t)((const char*)jobs[i].dev_ptr - lo), jobs[i].bytes, jobs[i].file_off });
             f->outstanding++;
             g.jobs_outstanding++;
-            g.stage_q.push_back(StageJob { fd, (const char*)jobs[i].dev_ptr, jobs[i].bytes, jobs[i].file_off, f });
+            g.stage_q.push_back(std::move(job));
             }
+        else
+            for (int i = 0; i < njobs; i++)
+                {
+                if (jobs[i].bytes == 0)
+                    continue;
+                f->outstanding++;
+                g.jobs_outstanding++;
+                g.stage_q.push_back(StageJob { fd, (const char*)jobs[i].dev_ptr, jobs[i].bytes, jobs[i].file_off, f, {} });
+                }
         f->assembling = false;
-        g.cur = nullptr;
         }
     g.cv_stage.notify_all();
+    g.cv_done.notify_all(); // a frame without jobs is free again at once
     return 0;
+    }
+
+// a handle gives up the frame it was assembling (close / error paths): the arena may be recycled
+void dev_frame_abandon(void* frame)
+    {
+    ArenaFrame* f = (ArenaFrame*)frame;
+    if (f == nullptr)
+        return;
+        {
+        std::lock_guard<std::mutex> lk(g.mu);
+        f->assembling = false;
+        }
+    g.cv_done.notify_all();
     }
 
 int dev_drain()

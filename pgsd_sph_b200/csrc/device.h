@@ -32,6 +32,9 @@ struct DevStats
     uint64_t file_bytes_written = 0;
     uint64_t file_bytes_read = 0;
     double commit_wait_s = 0;
+    double d2h_busy_s = 0;  // sum over staged pieces of their D2H copy time (CUDA events on the copy streams)
+    double file_busy_s = 0; // sum over staged pieces of the writer thread's time inside the file write
+    uint64_t pieces = 0;    // staged pieces
     };
 DevStats& dev_stats();
 
@@ -44,6 +47,8 @@ bool dev_is_device_pointer(const void* p);
 void dev_set_user_stream(void* s);
 void* dev_user_stream();
 int dev_configure_staging(uint32_t n_slots, uint64_t slot_bytes, uint32_t writer_threads);
+void dev_file_stage_config(int* writers, int* pwrite_threads, int* mode); // writer threads, pwrite pieces in flight, FileMode
+uint64_t dev_slot_bytes();
 void dev_shutdown(); // drain, stop threads, free device/pinned memory
 
 size_t type_size(int pgsd_type); // 0 for unknown
@@ -62,8 +67,10 @@ struct PackRequest
     bool host_columns;
     void* arena_ptr; // out: packed chunk in the current frame arena (NULL when N == 0)
     };
-// Packs all requests with ONE K1 launch on the user stream into fresh arena allocations.
-int dev_arena_pack(PackRequest* reqs, int n);
+// Packs all requests with ONE K1 launch on the user stream into fresh allocations of the frame arena *frame
+// (NULL: a free arena is acquired -- waiting for one when max_frames packed frames are still on their way to the
+// file -- and returned).  The arena belongs to the calling file handle until it is submitted or abandoned.
+int dev_arena_pack(PackRequest* reqs, int n, void** frame);
 
 // ---- K3: arena -> pinned ring -> pwrite(fd) on writer threads --------------------------
 struct WriteJob
@@ -74,7 +81,8 @@ struct WriteJob
     };
 // Queue the jobs of the frame being assembled and retire its arena; returns at once (the
 // arena memory is recycled when its last byte is on its way to the file).
-int dev_frame_submit(int fd, const WriteJob* jobs, int njobs);
+int dev_frame_submit(int fd, const WriteJob* jobs, int njobs, void* frame);
+void dev_frame_abandon(void* frame);
 int dev_drain(); // wait for every queued file write; PGSD_ERROR_IO (-1) if one failed
 int dev_copy_to_host(void* host_dst, const void* dev_src, uint64_t bytes); // synchronous
 // file -> pinned double buffer -> device (read path)

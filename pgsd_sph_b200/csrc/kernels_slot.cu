@@ -1037,11 +1037,25 @@ int dev_reorder_distributed(uint64_t n_local, const uint32_t* keys, uint64_t out
         set_last_error("reorder_distributed: at most 8 ranks");
         return -2;
         }
-    if (nfields < 0 || (nfields > 0 && fields == nullptr) || n_out == nullptr || nfields + 1 > SLOT_MAX_FIELDS
-        || (n_local > 0 && keys == nullptr) || ((uintptr_t)keys & 15u) != 0)
+    if (n_out == nullptr)
+        {
+        set_last_error("reorder_distributed: n_out is required");
+        return -2;
+        }
+    // Rank-local argument problems must not make this rank leave before the collectives below (its peers would wait
+    // for it forever): they are folded into the first all-gather and every rank returns the same error.
+    // n_local == UINT64_MAX: the caller already knows its arguments are unusable and only takes part.
+    bool bad_args = false;
+    if (n_local == 0xffffffffffffffffull)
+        {
+        bad_args = true;
+        n_local = 0;
+        }
+    if (nfields < 0 || (nfields > 0 && fields == nullptr) || nfields + 1 > SLOT_MAX_FIELDS || (n_local > 0 && keys == nullptr)
+        || ((uintptr_t)keys & 15u) != 0)
         {
         set_last_error("reorder_distributed: bad arguments (keys must be 16-byte aligned)");
-        return -2;
+        bad_args = true;
         }
     cudaStream_t st = (cudaStream_t)stream_v;
     SlotArgs a;
@@ -1052,14 +1066,15 @@ int dev_reorder_distributed(uint64_t n_local, const uint32_t* keys, uint64_t out
     a.f[nf++] = SlotField { keys, keys_sorted, 1u, off };
     off += 1;
     in_words += 1;
-    for (int i = 0; i < nfields; i++)
+    for (int i = 0; i < nfields && !bad_args; i++)
         {
         const ReorderField& f = fields[i];
         if (f.row_bytes == 0 || f.row_bytes % 4 != 0 || (((uintptr_t)f.in | (uintptr_t)f.out) & 3u) != 0
             || (n_local > 0 && f.in == nullptr) || (out_capacity > 0 && f.out == nullptr))
             {
             set_last_error("reorder_distributed: fields must be word sized and word aligned");
-            return -2;
+            bad_args = true;
+            break;
             }
         if (((uintptr_t)f.in & 15u) != 0)
             aligned = false;
@@ -1070,7 +1085,12 @@ int dev_reorder_distributed(uint64_t n_local, const uint32_t* keys, uint64_t out
     if (off > SLOT_MAX_ROW_WORDS)
         {
         set_last_error("reorder_distributed: rows of at most 31 words");
-        return -2;
+        bad_args = true;
+        }
+    if (bad_args)
+        {
+        n_local = 0; // nothing of this rank's data is touched
+        off = off > SLOT_MAX_ROW_WORDS || off == 0 ? 1 : off;
         }
     a.nfields = nf;
     a.row_words = off;
@@ -1096,15 +1116,27 @@ int dev_reorder_distributed(uint64_t n_local, const uint32_t* keys, uint64_t out
                 memcpy(w9, &h, 64);
             }
         };
-    uint64_t mine[12] = { n_local, out_capacity, (uint64_t)g_dist_copy_bytes };
+    constexpr size_t W1 = 13;
+    uint64_t mine[W1] = { n_local, out_capacity, (uint64_t)g_dist_copy_bytes };
     export_copy(mine + 3);
-    std::vector<uint64_t> all((size_t)G * 12);
-    if (c->allgather(mine, all.data(), 12) != 0)
+    mine[12] = bad_args ? 1 : 0;
+    std::vector<uint64_t> all((size_t)G * W1);
+    if (c->allgather(mine, all.data(), W1) != 0)
         return -1;
     trace.mark("allgather(sizes+handles)");
     uint64_t N = 0;
+    bool any_bad = false;
     for (int p = 0; p < G; p++)
-        N += all[(size_t)p * 12];
+        {
+        N += all[(size_t)p * W1];
+        any_bad = any_bad || all[(size_t)p * W1 + 12] != 0;
+        }
+    if (any_bad)
+        {
+        if (!bad_args)
+            set_last_error("reorder_distributed: another rank was called with invalid arguments");
+        return -2;
+        }
     *n_out = 0;
     if (id_first)
         *id_first = 0;
@@ -1159,19 +1191,22 @@ int dev_reorder_distributed(uint64_t n_local, const uint32_t* keys, uint64_t out
     const size_t copy_need = part ? up256((size_t)nbr * cap * a.row_words * 4) + 256 : lines_bytes;
     bool grow = false;
     for (int p = 0; p < G; p++)
-        if (all[(size_t)p * 12 + 2] < copy_need)
+        if (all[(size_t)p * W1 + 2] < copy_need)
             grow = true;
     std::vector<uint64_t> hall((size_t)G * 9);
     if (grow)
         {
         dist_close_peers();
-        if (cudaStreamSynchronize(st) != cudaSuccess || c->barrier() != 0) // nobody maps the old copies any more
+        const bool synced = cudaStreamSynchronize(st) == cudaSuccess; // a local failure is reported through the handle exchange
+        if (!synced)
+            cudaGetLastError();
+        if (c->barrier() != 0) // nobody maps the old copies any more
             return -1;
         if (g_dist_copy)
             cudaFree(g_dist_copy);
         g_dist_copy = nullptr;
         g_dist_copy_bytes = 0;
-        const bool ok = cudaMalloc(&g_dist_copy, copy_need) == cudaSuccess;
+        const bool ok = synced && cudaMalloc(&g_dist_copy, copy_need) == cudaSuccess;
         if (ok)
             g_dist_copy_bytes = copy_need;
         else
@@ -1183,7 +1218,7 @@ int dev_reorder_distributed(uint64_t n_local, const uint32_t* keys, uint64_t out
         }
     else
         for (int p = 0; p < G; p++)
-            memcpy(&hall[(size_t)p * 9], &all[(size_t)p * 12 + 3], 9 * sizeof(uint64_t));
+            memcpy(&hall[(size_t)p * 9], &all[(size_t)p * W1 + 3], 9 * sizeof(uint64_t));
     for (int p = 0; p < G; p++)
         if (hall[(size_t)p * 9 + 8] == 0)
             {
@@ -1337,7 +1372,7 @@ int dev_reorder_distributed(uint64_t n_local, const uint32_t* keys, uint64_t out
         return 1; // more ids than slots in a bucket: duplicates
     bool fits = true;
     for (int p = 0; p < G; p++)
-        if (owned[p] > all[(size_t)p * 12 + 1])
+        if (owned[p] > all[(size_t)p * W1 + 1])
             fits = false;
     if (!fits)
         {

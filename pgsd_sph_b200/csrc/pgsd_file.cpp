@@ -257,6 +257,7 @@ struct FileState
     std::vector<char> stage;
     std::vector<WriteJob> dev_jobs; // device chunks of the frame being assembled
     bool device_frame_open = false;
+    void* dev_frame = nullptr;      // this handle's frame arena (device.cu) while a frame is being assembled
     // rank-replicated view of the per-rank write buffers (ref: each rank's write_buffer.size)
     uint64_t root_wb_size = 0; // rank 0's write_buffer.size  (index locations refer to it)
     uint64_t wb_excl = 0;      // sum over ranks < rank of their write_buffer.size
@@ -350,8 +351,12 @@ void release_state(pgsd_handle* h)
     h->frame_names.n_names = 0;
     if (s)
         {
+        if (s->dev_frame)
+            dev_frame_abandon(s->dev_frame); // chunks packed for a frame that was never committed
         if (s->fd >= 0)
             close(s->fd);
+        if (s->comm)
+            comm_release();
         delete s;
         }
     h->fh = nullptr;
@@ -540,7 +545,10 @@ int submit_device_jobs(FileState* s)
     {
     if (!s->device_frame_open)
         return PGSD_SUCCESS;
-    int rc = dev_frame_submit(s->fd, s->dev_jobs.data(), (int)s->dev_jobs.size());
+    int rc = dev_frame_submit(s->fd, s->dev_jobs.data(), (int)s->dev_jobs.size(), s->dev_frame);
+    if (rc != 0)
+        dev_frame_abandon(s->dev_frame);
+    s->dev_frame = nullptr;
     s->dev_jobs.clear();
     s->device_frame_open = false;
     return rc;
@@ -866,7 +874,7 @@ int file_write_chunks_device(pgsd_handle* h, int n, const DeviceChunk* chunks)
         const DeviceChunk& c = chunks[i];
         reqs[(size_t)i] = PackRequest { c.dst_type, c.src_type, c.N, c.M, c.cols, c.host_columns, nullptr };
         }
-    int rc = dev_arena_pack(reqs.data(), n);
+    int rc = dev_arena_pack(reqs.data(), n, &s->dev_frame);
     if (rc != 0)
         return rc;
     s->device_frame_open = true;
@@ -920,6 +928,7 @@ int pgsd_create_and_open(struct pgsd_handle* handle, const char* fname, const ch
         handle->open_flags = flags;
     FileState* s = new FileState;
     s->comm = comm();
+    comm_acquire();
     handle->fh = s;
 
     int rc = PGSD_SUCCESS;
@@ -978,6 +987,7 @@ int pgsd_open(struct pgsd_handle* handle, const char* fname, enum pgsd_open_flag
     handle->open_flags = flags;
     FileState* s = new FileState;
     s->comm = comm();
+    comm_acquire();
     handle->fh = s;
     s->fd = open(fname, flags == PGSD_OPEN_READONLY ? O_RDONLY : O_RDWR);
     int rc = s->fd < 0 ? PGSD_ERROR_IO : initialize_handle(handle);

@@ -229,6 +229,24 @@ class _HOOMDTrajectoryView(object):
 ID_CHUNK = 'log/particles/id'  # particle id has no schema slot; SURVEY.md section 7 decision
 
 
+def _packed_device_field(name, obj, n):
+    """(ptr, shape, dtype, keepalive) of a device array that the reorder kernels can read as n packed rows."""
+    from .devmem import as_device_view
+    ptr, shape, dt, strides, keep = as_device_view(obj)
+    rows = int(shape[0]) if len(shape) else 1
+    if rows != n:
+        raise ValueError(f"field {name} has {rows} rows, expected {n}")
+    if strides is not None:
+        want, acc = [], dt.itemsize
+        for d in reversed(shape):
+            want.append(acc)
+            acc *= int(d)
+        if tuple(strides) != tuple(reversed(want)) and n > 1:
+            raise ValueError(f"field {name} is not C-contiguous on the device (strides {tuple(strides)}); "
+                             "copy it to a packed array first")
+    return ptr, shape, dt, keep
+
+
 def reorder_by_id(ids, arrays, device=False):
     """Reorder per-particle arrays into particle-ID order on the GPU (K4 + K5).
 
@@ -248,7 +266,7 @@ def reorder_by_id(ids, arrays, device=False):
         sorted_ids = DeviceArray((n,), numpy.uint32)
         outs, fields, keeps = {}, (_lib.Field * max(len(names), 1))(), [keep]
         for i, k in enumerate(names):
-            ptr, shape, dt, strides, kp = as_device_view(arrays[k])
+            ptr, shape, dt, kp = _packed_device_field(k, arrays[k], n)
             keeps.append(kp)
             row = dt.itemsize * (int(numpy.prod(shape[1:])) if len(shape) > 1 else 1)
             outs[k] = DeviceArray(shape, dt)
@@ -307,13 +325,23 @@ def reorder_by_id_distributed(ids, arrays):
     cap = int(cap.value)
     sorted_ids = DeviceArray((cap,), numpy.uint32)
     outs, fields, keeps = {}, (_lib.Field * max(len(names), 1))(), [keep]
+    bad = None
     for i, k in enumerate(names):
-        ptr, shape, dt, strides, kp = as_device_view(arrays[k])
+        try:
+            ptr, shape, dt, kp = _packed_device_field(k, arrays[k], n)
+        except ValueError as e:   # the call below is collective: a rank must not leave before it
+            bad = bad or e
+            ptr, shape, dt, _, kp = as_device_view(arrays[k])
         keeps.append(kp)
         row = dt.itemsize * (int(numpy.prod(shape[1:])) if len(shape) > 1 else 1)
         outs[k] = DeviceArray((cap,) + tuple(shape[1:]), dt)
         fields[i] = _lib.Field(ptr, outs[k].ptr, row)
     n_out, id_first = C.c_uint64(), C.c_uint64()
+    if bad is not None:
+        # take part in the collective with an empty partition flagged as invalid: every rank gets the error
+        lib.pgsd_b200_reorder_distributed(0xffffffffffffffff, kptr, cap, C.byref(n_out), C.byref(id_first), sorted_ids.ptr,
+                                          len(names), fields, None)
+        raise bad
     rc = lib.pgsd_b200_reorder_distributed(n, kptr, cap, C.byref(n_out), C.byref(id_first), sorted_ids.ptr, len(names),
                                            fields, None)
     if rc == 1:
@@ -608,6 +636,9 @@ class HOOMDTrajectory(object):
                         container.__dict__[name] = initial.__dict__[name]
                         if initial.__dict__.get('_isdefault_' + name):
                             container.__dict__['_isdefault_' + name] = True
+                        elif path == 'particles':
+                            # rows are in FRAME 0's storage order, not this frame's (see _reordered)
+                            container.__dict__['_fallback_' + name] = True
                     else:
                         # the reference fills an N-row array with the default and marks it read-only
                         # (hoomd.py:871-881) -- 76 B/particle of constants per frame 0; a zero-stride
@@ -626,6 +657,7 @@ class HOOMDTrajectory(object):
                     snap.log[log[4:]] = self.file.read_chunk(frame=idx, name=log, offset=0, r_all=False)
             elif self._initial_frame is not None and log[4:] in self._initial_frame.log:
                 snap.log[log[4:]] = self._initial_frame.log[log[4:]]
+                snap.__dict__.setdefault('_log_fallback', set()).add(log[4:])
 
         for v in ahead.values():  # prefetched but unused (should not happen)
             v.free()
@@ -635,6 +667,12 @@ class HOOMDTrajectory(object):
         if self._reorder == 'id':
             return self._reordered(snap)
         return snap
+
+    def _initial_reordered(self):
+        """Frame 0 in particle-ID order (host arrays unless device=True), computed once: the source of fallback fields."""
+        if getattr(self, '_initial_sorted', None) is None:
+            self._initial_sorted = self._reordered(self._initial_frame)
+        return self._initial_sorted
 
     def _reordered(self, snap):
         """Particle-ID order: every array with one row per particle is gathered by the stable
@@ -650,16 +688,28 @@ class HOOMDTrajectory(object):
         out.particles.N = snap.particles.N
         out.particles.types = snap.particles.types
         out.particles.type_shapes = snap.particles.type_shapes
+        # Per-particle arrays that fell back to frame 0 (chunk absent in this frame) are in frame 0's storage order:
+        # gathering them with THIS frame's permutation would attach them to the wrong particles whenever the storage
+        # order changed in between (particle migration between ranks).  They are taken from frame 0's own ID-ordered
+        # result instead; that needs this frame to carry its own ids (otherwise frame 0's ids order everything).
+        log_fb = snap.__dict__.get('_log_fallback', set())
+        own_ids = ID_CHUNK[4:] not in log_fb
+        first = self._initial_reordered() if (own_ids and snap is not self._initial_frame) else None
         todo = {}
         for name in _PARTICLE_FIELDS:
             v = snap.particles.__dict__[name]
             if snap.particles.__dict__.get('_isdefault_' + name):
                 out.particles.__dict__[name] = v
+            elif first is not None and snap.particles.__dict__.get('_fallback_' + name):
+                out.particles.__dict__[name] = first.particles.__dict__[name]
             else:
                 todo['p:' + name] = v
         for k, v in snap.log.items():
             if k.startswith('particles/') and k != ID_CHUNK[4:] and len(v) == N:
-                todo['l:' + k] = v
+                if first is not None and k in log_fb:
+                    out.log[k] = first.log[k]
+                else:
+                    todo['l:' + k] = v
             else:
                 out.log[k] = v
         if self._read_device:

@@ -199,3 +199,17 @@ def test_reorder_distributed_plan_tiles_the_id_space():
     assert lib.pgsd_b200_reorder_distributed_plan(1 << 32, 2, 0, C.byref(bad), C.byref(bad)) < 0
     assert lib.pgsd_b200_reorder_distributed_plan(1000, 9, 0, C.byref(bad), C.byref(bad)) < 0
     assert lib.pgsd_b200_reorder_distributed_plan(1000, 2, 2, C.byref(bad), C.byref(bad)) < 0
+
+
+def test_communicator_cannot_be_replaced_while_files_are_open(tmp_path):
+    """Open handles keep a pointer to the communicator they were opened under: replacing it is refused
+    until they are closed."""
+    from pgsd_sph_b200 import _lib
+    lib = _lib.load()
+    f = fl.open(str(tmp_path / "c.gsd"), 'w', 'pgsd-b200', 'hoomd', [1, 4])
+    assert lib.pgsd_b200_comm_finalize() == -2
+    assert b"still open" in lib.pgsd_b200_last_error()
+    f.write_chunk("a", np.arange(4, dtype=np.uint32), write_all=False)
+    f.end_frame()
+    f.close()
+    assert lib.pgsd_b200_comm_finalize() == 0

@@ -1,6 +1,8 @@
 // pwrite_bench.cpp -- host-side ceiling of the K3 file stage: T threads pwrite()ing fixed-size
 // pieces of one new file (page cache / tmpfs), the way libpgsd_b200's writer threads do.
-//   pwrite_bench <path> <total_MiB> <piece_MiB> <threads> [mode]   mode: pwrite | mmap | falloc
+//   pwrite_bench <path> <total_MiB> <piece_MiB> <threads> [mode]
+//   mode: pwrite | mmap | falloc | mmap_piece[_pop] | falloc_piece[_pop] (whole piece allocated with one fallocate
+//   before it is mapped; _pop: MADV_POPULATE_WRITE before the copy)
 // Prints one line: threads piece mode GB/s.  Measurement tool only; not part of the library.
 #include <atomic>
 #include <chrono>
@@ -42,7 +44,8 @@ int main(int argc, char** argv)
             perror("fallocate");
         }
     const bool populate = (mode == "mmap_pop");
-    const bool piecewise = (mode == "mmap_piece" || mode == "mmap_piece_pop");
+    const bool bulk_falloc = (mode == "falloc_piece" || mode == "falloc_piece_pop");
+    const bool piecewise = (mode == "mmap_piece" || mode == "mmap_piece_pop" || bulk_falloc);
     if (mode == "mmap" || mode == "mmap_pop")
         {
         if (ftruncate(fd, (off_t)total) != 0)
@@ -62,10 +65,10 @@ int main(int argc, char** argv)
                 if (piecewise)
                     {
                     // what a writer thread of the library would do: extend, map the piece, copy, unmap
-                    if (fallocate(fd, 0, (off_t)(off + len - 1), 1) != 0)
+                    if (bulk_falloc ? fallocate(fd, 0, (off_t)off, (off_t)len) != 0 : fallocate(fd, 0, (off_t)(off + len - 1), 1) != 0)
                         perror("fallocate");
                     char* m = (char*)mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_SHARED, fd, (off_t)off);
-                    if (mode == "mmap_piece_pop")
+                    if (mode == "mmap_piece_pop" || mode == "falloc_piece_pop")
                         madvise(m, len, 23 /* MADV_POPULATE_WRITE */);
                     memcpy(m, src[(size_t)t], len);
                     munmap(m, len);
