@@ -802,16 +802,20 @@ def run_frames_leg(lib, dist, args, windows, n_total, frames, nlogs, tag):
         with fl.open(path, 'w', 'pgsd-b200', 'hoomd', [1, 4]) as f:
             prep = f.prepare_frame_soa([(nm, [src[j] for j in idx], dt, rows, True) for nm, idx, dt in SOA_CHUNKS],
                                        rank=dist.rank)
-            scal = [synth.frame_scalars(n_total, i) for i in range(frames)]
+            # the per-frame scalars live in buffers that are updated in place (what a simulation loop does): their
+            # pgsd_write_chunk arguments are validated once (PGSDFile.prepare_chunks)
+            scal = synth.frame_scalars(n_total, 0)
+            step = scal[0][1]
+            head = f.prepare_chunks([(k, a, None, False) for k, a in scal])
+            tail = f.prepare_chunks([(k, a, None, False) for k, a in logs])
             lib.pgsd_b200_reset_stats()
             dist.barrier()
             w0 = time.perf_counter()
             for i in range(frames):
-                for k, a in scal[i]:
-                    f.write_chunk(k, a, write_all=False)
+                step[0] = 10 * i
+                f.write_prepared(head)
                 f.write_frame_soa(prep)
-                for k, a in logs:
-                    f.write_chunk(k, a, write_all=False)
+                f.write_prepared(tail)
                 f.end_frame()
             f.flush()
             dt_ = time.perf_counter() - w0

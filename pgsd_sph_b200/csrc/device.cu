@@ -10,6 +10,7 @@
 #include "device_internal.h"
 #include "file_stage.h"
 
+#include <nvtx3/nvToolsExt.h> // header-only; ranges cost nothing unless a profiler (nsys) is attached
 #include <nccl.h> // types only; the library is dlopen()ed so that CPU-only hosts can load us
 
 #include <atomic>
@@ -254,6 +255,7 @@ void writer_main(int widx)
                 g.cv_pwrite.wait(lk, [] { return g.pwrite_active < g.pwrite_threads; });
                 g.pwrite_active++;
                 }
+            nvtxRangePushA("pgsd K3 file piece");
             const auto t0 = std::chrono::steady_clock::now();
             if (g.trace_on)
                 ft0 = trace_now_us();
@@ -297,6 +299,7 @@ void writer_main(int widx)
             if (g.trace_on)
                 ft1 = trace_now_us();
             busy = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            nvtxRangePop();
             if (!use_mmap)
                 {
                     {
@@ -392,11 +395,13 @@ void stager_main()
                 }
             const int si = (int)(rr++ & 1);
             cudaStream_t st = g.copy[si];
+            nvtxRangePushA("pgsd K3 D2H piece (enqueue)");
             bool ok = cudaStreamWaitEvent(st, job.frame->packed, 0) == cudaSuccess
                       && cudaEventRecord(g.slots[slot].t0, st) == cudaSuccess
                       && cudaMemcpyAsync(g.slots[slot].host, job.dev + done, len, cudaMemcpyDeviceToHost, st)
                              == cudaSuccess
                       && cudaEventRecord(g.slots[slot].t1, st) == cudaSuccess;
+            nvtxRangePop();
             if (!ok)
                 g.io_error = true;
                 {
@@ -888,7 +893,9 @@ int dev_arena_pack(PackRequest* reqs, int n, void** frame_io)
             }
         if (g.trace_on)
             cudaEventRecord(f->k1[0], g.user);
+        nvtxRangePushA("pgsd K1 pack");
         rc = pack_launch(segs, ns, g.user);
+        nvtxRangePop();
         if (rc != 0)
             return rc;
         if (g.trace_on)
@@ -1417,7 +1424,10 @@ Comm* make_nccl_comm(int rank, int nprocs, const void* unique_id, int device, st
 int dev_reorder(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, uint32_t* perm, int nfields,
                 const ReorderField* fields, void* stream)
     {
-    return dev_reorder_rows(n, keys, keys_sorted, perm, nfields, fields, stream);
+    nvtxRangePushA("pgsd K4+K5 reorder");
+    const int rc = dev_reorder_rows(n, keys, keys_sorted, perm, nfields, fields, stream);
+    nvtxRangePop();
+    return rc;
     }
 
 // ------------------------------------------------------------------------------ reorder, host buffers

@@ -339,6 +339,8 @@ __global__ void __launch_bounds__(NT) k6_part_scatter(uint64_t n, int L, uint32_
     __shared__ uint32_t col[SLOT_MAX_ROW_WORDS];
     __shared__ uint32_t scnt[8], sofs[9], sbase[8];
     uint32_t* raw = reinterpret_cast<uint32_t*>(smem_raw);
+    if (flag[0] != 0) // set before this kernel starts (kd_plan: the step was called off on every rank): uniform
+        return;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const uint64_t tile0 = (uint64_t)blockIdx.x * T;
     const uint32_t tile_n = (uint32_t)((n - tile0) < (uint64_t)T ? (n - tile0) : T);
@@ -464,15 +466,22 @@ __global__ void __launch_bounds__(NT) k6_part_scatter(uint64_t n, int L, uint32_
 // One bulk copy per tile; bucket = key bits above the slot bits minus this rank's first bucket; positions from the
 // local cursors; records go into the "lines" copy k6_slot_place reads.
 template <int T, int NT>
-__global__ void __launch_bounds__(NT) k6_slot_scatter_rec(const uint32_t* __restrict__ rec, uint64_t n, int L, uint32_t bmask,
+__global__ void __launch_bounds__(NT) k6_slot_scatter_rec(const uint32_t* __restrict__ rec, uint64_t n_host,
+                                                         const uint32_t* __restrict__ n_dev, int L, uint32_t bmask,
                                                          uint32_t bucket0, uint32_t* __restrict__ cursor, uint32_t cstride,
                                                          uint32_t* __restrict__ aos, uint32_t* __restrict__ flag,
                                                          const __grid_constant__ SlotArgs args)
     {
+    // n_dev != NULL: the row count was decided on the device (kd_plan); the grid covers the largest possible inbox
+    const uint64_t n = n_dev ? (uint64_t)*n_dev : n_host;
+    if ((uint64_t)blockIdx.x * T >= n)
+        return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bar_mem;
     __shared__ uint32_t col[SLOT_MAX_ROW_WORDS];
     uint32_t* rows = reinterpret_cast<uint32_t*>(smem_raw); // T records of RW words
+    if (flag[0] != 0)
+        return;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const uint64_t tile0 = (uint64_t)blockIdx.x * T;
     const uint32_t tile_n = (uint32_t)((n - tile0) < (uint64_t)T ? (n - tile0) : T);
@@ -690,6 +699,273 @@ __global__ void __launch_bounds__(1024) k6_slot_place(const uint32_t* __restrict
                 }
         }
     }
+// ---- distributed reorder without the host in the loop ------------------------------------------------------------
+// Every rank's IPC-exported buffer starts with a control block and two parity copies of a count table; the ranks
+// exchange their per-bucket counts, "my records have arrived" and "my buckets are placed" by plain stores into the
+// peers' buffers (NVLink) followed by a system-scope release of a flag word that the peer's next kernel spins on.
+// Parity = call number & 1: a rank can be at most one call ahead of a peer it has not heard from, so two copies
+// suffice.  Flags carry the call number (epoch); a wait gives up after ~2 s worth of cycles and reports it.
+struct DistCtl
+    {
+    uint32_t ready[2][8]; // [parity][source rank]: counts published
+    uint32_t done[2][8];  // records of the source rank have reached my inbox
+    uint32_t fin[2][8];   // the source rank has placed its buckets ...
+    uint32_t dup[2][8];   // ... and found (1) / did not find (0) two records with one id
+    };
+constexpr size_t DIST_CTL_BYTES = 4096;
+constexpr uint32_t DIST_ROW_WORDS = (1u << SLOT_MAX_BUCKET_BITS) + 8; // counts + {n_local lo, hi, out_capacity lo, hi, status}
+constexpr size_t DIST_HDR_BYTES = DIST_CTL_BYTES + (size_t)2 * 8 * DIST_ROW_WORDS * 4; // in front of the inbox
+static_assert(sizeof(DistCtl) <= DIST_CTL_BYTES && DIST_HDR_BYTES % 256 == 0, "header layout");
+
+struct DistPeers
+    {
+    void* shared[8]; // base of every rank's buffer (own memory or IPC mapping)
+    };
+__device__ __forceinline__ uint32_t* dist_row(void* shared, int par, int src)
+    {
+    return reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(shared) + DIST_CTL_BYTES) + ((size_t)par * 8 + src) * DIST_ROW_WORDS;
+    }
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v)
+    {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    }
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p)
+    {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+    }
+__device__ __forceinline__ bool dist_spin(const uint32_t* p, uint32_t epoch)
+    {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(p) != epoch)
+        {
+        if (clock64() - t0 > 4000000000ll)
+            return false;
+        __nanosleep(200);
+        }
+    return true;
+    }
+
+// status bits of a distributed call (device words and the pinned result the host reads at the end)
+enum : uint32_t
+    {
+    DST_RANGE = 1,    // an id outside [0, buckets * 2^L)
+    DST_OVERFLOW = 2, // more ids than slots in a bucket: duplicates
+    DST_RESOURCE = 4, // a rank could not allocate / map memory
+    DST_FITS = 8,     // out_capacity too small on some rank
+    DST_TIMEOUT = 16, // a peer never signalled
+    DST_DUP = 32      // two records of a bucket share a slot
+    };
+
+// block p: my counts + meta into rank p's table, then the flag
+__global__ void __launch_bounds__(256) kd_publish(DistPeers peers, int me, int par, uint32_t epoch, const uint32_t* __restrict__ counts,
+                                                 uint32_t nbp, const uint32_t* __restrict__ flag, uint64_t n_local,
+                                                 uint64_t out_capacity, uint32_t status0)
+    {
+    void* dst = peers.shared[blockIdx.x];
+    if (dst == nullptr) // this peer could not be mapped: it will report a timeout
+        return;
+    uint32_t* row = dist_row(dst, par, me);
+    for (uint32_t i = threadIdx.x; i < nbp; i += blockDim.x)
+        row[i] = counts[i];
+    if (threadIdx.x == 0)
+        {
+        row[nbp + 0] = (uint32_t)n_local;
+        row[nbp + 1] = (uint32_t)(n_local >> 32);
+        row[nbp + 2] = (uint32_t)out_capacity;
+        row[nbp + 3] = (uint32_t)(out_capacity >> 32);
+        row[nbp + 4] = status0 | (flag[2] != 0 ? DST_RANGE : 0u);
+        }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0)
+        st_release_sys(&reinterpret_cast<DistCtl*>(dst)->ready[par][me], epoch);
+    }
+
+// One CTA: waits for the counts of all ranks, then decides everything the host used to decide -- identically on
+// every rank: who owns how many rows, whether a bucket overflows, where my run starts in every owner's inbox,
+// the output rows of my buckets.
+__global__ void __launch_bounds__(1024) kd_plan(void* myshared, int G, int me, int par, uint32_t epoch, uint32_t nbp, uint32_t nb_used,
+                                               uint32_t nbr, uint32_t cap, uint32_t* __restrict__ owner_cursor,
+                                               uint32_t* __restrict__ base, uint32_t* __restrict__ n_owned, uint32_t* __restrict__ flag,
+                                               uint32_t* __restrict__ host_out)
+    {
+    extern __shared__ uint32_t tot[]; // nbr + 1: rows of my buckets
+    __shared__ uint32_t s_status, s_all[8], s_low[8], wsum[32], s_red[2][32];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    DistCtl* ctl = reinterpret_cast<DistCtl*>(myshared);
+    if (tid == 0)
+        s_status = 0;
+    __syncthreads();
+    if (tid < G && !dist_spin(&ctl->ready[par][tid], epoch))
+        atomicOr(&s_status, (uint32_t)DST_TIMEOUT);
+    __syncthreads();
+    const uint32_t* rows[8];
+    for (int p = 0; p < 8; p++)
+        rows[p] = dist_row(myshared, par, p < G ? p : 0);
+    if (tid < G)
+        atomicOr(&s_status, rows[tid][nbp + 4]);
+    const uint32_t my_b0 = min((uint32_t)me * nbr, nb_used), my_b1 = min(my_b0 + nbr, nb_used);
+    uint32_t bad = 0;
+    for (int o = 0; o < G; o++)
+        {
+        const uint32_t b0 = min((uint32_t)o * nbr, nb_used), b1 = min(b0 + nbr, nb_used);
+        uint32_t all = 0, low = 0;
+        for (uint32_t b = b0 + tid; b < b1; b += 1024)
+            {
+            uint32_t t = 0;
+            for (int p = 0; p < G; p++)
+                {
+                const uint32_t c = rows[p][b];
+                t += c;
+                if (p < me)
+                    low += c;
+                }
+            all += t;
+            if (t > cap)
+                bad |= DST_OVERFLOW;
+            if (o == me)
+                tot[b - my_b0] = t;
+            }
+        all = __reduce_add_sync(0xffffffffu, all);
+        low = __reduce_add_sync(0xffffffffu, low);
+        if (lane == 0)
+            {
+            s_red[0][w] = all;
+            s_red[1][w] = low;
+            }
+        __syncthreads();
+        if (tid == 0)
+            {
+            uint32_t a2 = 0, l2 = 0;
+            for (int i = 0; i < 32; i++)
+                {
+                a2 += s_red[0][i];
+                l2 += s_red[1][i];
+                }
+            s_all[o] = a2;
+            s_low[o] = l2;
+            }
+        __syncthreads();
+        }
+    for (uint32_t b = nb_used + tid; b < nbp; b += 1024) // ids beyond the last used bucket (the histogram flags them too)
+        for (int p = 0; p < G; p++)
+            if (rows[p][b])
+                bad |= DST_RANGE;
+    if (bad)
+        atomicOr(&s_status, bad);
+    if (tid < G)
+        {
+        const unsigned long long capo = (unsigned long long)rows[tid][nbp + 2] | ((unsigned long long)rows[tid][nbp + 3] << 32);
+        if ((unsigned long long)s_all[tid] > capo)
+            atomicOr(&s_status, (uint32_t)DST_FITS);
+        }
+    // exclusive prefix of my buckets' rows -> base[0 .. nbr + 1] (entries past my last bucket repeat the total)
+    const uint32_t nmine = my_b1 - my_b0;
+    const uint32_t per = (nbr + 2 + 1023u) / 1024u;
+    const uint32_t i0 = (uint32_t)tid * per;
+    uint32_t sum = 0;
+    for (uint32_t i = 0; i < per; i++)
+        if (i0 + i < nmine)
+            sum += tot[i0 + i];
+    uint32_t inc = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+        {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d)
+            inc += t;
+        }
+    if (lane == 31)
+        wsum[w] = inc;
+    __syncthreads();
+    if (w == 0)
+        {
+        const uint32_t v = wsum[lane];
+        uint32_t iv = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+            {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, iv, d);
+            if (lane >= d)
+                iv += t;
+            }
+        wsum[lane] = iv - v;
+        }
+    __syncthreads();
+    uint32_t run = wsum[w] + inc - sum;
+    for (uint32_t i = 0; i < per; i++)
+        {
+        const uint32_t k = i0 + i;
+        if (k <= nbr + 1)
+            {
+            base[k] = run;
+            if (k < nmine)
+                run += tot[k];
+            }
+        }
+    if (tid < 8)
+        owner_cursor[tid] = tid < G ? s_low[tid] : 0u;
+    __syncthreads();
+    if (tid == 0)
+        {
+        const uint32_t st = s_status;
+        *n_owned = st ? 0u : s_all[me];
+        flag[0] = st ? 1u : 0u; // the kernels that follow do nothing then
+        host_out[0] = st;
+        host_out[1] = s_all[me];
+        __threadfence_system();
+        }
+    }
+
+// lanes p < G: tell rank p that my part of the step is complete (which = 0: records delivered, 1: buckets placed)
+__global__ void kd_signal(DistPeers peers, int G, int me, int par, uint32_t epoch, int which, const uint32_t* __restrict__ flag)
+    {
+    const int p = threadIdx.x;
+    if (p >= G || peers.shared[p] == nullptr)
+        return;
+    DistCtl* ctl = reinterpret_cast<DistCtl*>(peers.shared[p]);
+    __threadfence_system();
+    if (which == 0)
+        st_release_sys(&ctl->done[par][me], epoch);
+    else
+        {
+        ctl->dup[par][me] = flag[1];
+        __threadfence_system();
+        st_release_sys(&ctl->fin[par][me], epoch);
+        }
+    }
+
+// lanes p < G wait for rank p's signal; which = 1 also folds the peers' duplicate flags into the result the host reads
+__global__ void kd_wait(void* myshared, int G, int par, uint32_t epoch, int which, uint32_t* __restrict__ flag, uint32_t* __restrict__ host_out)
+    {
+    const int p = threadIdx.x;
+    DistCtl* ctl = reinterpret_cast<DistCtl*>(myshared);
+    uint32_t st = 0;
+    if (p < G)
+        {
+        if (!dist_spin(which == 0 ? &ctl->done[par][p] : &ctl->fin[par][p], epoch))
+            st |= DST_TIMEOUT;
+        else if (which == 1)
+            {
+            const uint32_t d = ctl->dup[par][p];
+            if (d == 3)
+                st |= DST_RESOURCE;
+            else if (d != 0)
+                st |= DST_DUP;
+            }
+        }
+    st = __reduce_or_sync(0xffffffffu, st);
+    if (p == 0)
+        {
+        if (st & DST_TIMEOUT)
+            flag[0] = 1;
+        host_out[2 + which] = st;
+        __threadfence_system();
+        }
+    }
+
 // cursors of the distributed reorder: cursor[b * cstride] = first position of this rank's records in bucket b
 __global__ void k6_slot_spread(const uint32_t* __restrict__ start, uint32_t nb, uint32_t* __restrict__ cursor, uint32_t cstride)
     {
@@ -972,7 +1248,9 @@ int dev_reorder_slot(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, ui
 //   4 owner: [partition: k6_slot_scatter_rec inbox -> bucketed copy] k6_slot_place; all-gather of the duplicate flags
 // Requires unique ids below ceil(N / 2^L) * 2^L (dense ids 0..N-1 qualify); otherwise every rank returns 1
 // and the caller gathers the frame to one GPU and uses pgsd_b200_reorder_device.
-static void* g_dist_copy = nullptr; // this rank's part of the interleaved copy (IPC-exported)
+static void* g_dist_copy = nullptr; // this rank's IPC-exported buffer: [DistCtl + count tables (DIST_HDR_BYTES)][inbox / bucketed copy]
+static uint32_t g_dist_epoch = 0;   // calls that reached the exchange; the same on every rank
+static inline void* dist_inbox(void* base) { return base ? (void*)((unsigned char*)base + DIST_HDR_BYTES) : nullptr; }
 static size_t g_dist_copy_bytes = 0;
 static void* g_dist_peer[8] = { nullptr };
 static cudaIpcMemHandle_t g_dist_peer_handle[8];
@@ -1191,7 +1469,7 @@ int dev_reorder_distributed(uint64_t n_local, const uint32_t* keys, uint64_t out
     const size_t copy_need = part ? up256((size_t)nbr * cap * a.row_words * 4) + 256 : lines_bytes;
     bool grow = false;
     for (int p = 0; p < G; p++)
-        if (all[(size_t)p * W1 + 2] < copy_need)
+        if (all[(size_t)p * W1 + 2] < copy_need + DIST_HDR_BYTES)
             grow = true;
     std::vector<uint64_t> hall((size_t)G * 9);
     if (grow)
@@ -1206,10 +1484,15 @@ int dev_reorder_distributed(uint64_t n_local, const uint32_t* keys, uint64_t out
             cudaFree(g_dist_copy);
         g_dist_copy = nullptr;
         g_dist_copy_bytes = 0;
-        const bool ok = synced && cudaMalloc(&g_dist_copy, copy_need) == cudaSuccess;
+        bool ok = synced && cudaMalloc(&g_dist_copy, copy_need + DIST_HDR_BYTES) == cudaSuccess;
         if (ok)
-            g_dist_copy_bytes = copy_need;
-        else
+            {
+            // flags of the new buffer start at 0 (no call number is 0); the handle exchange below is also the barrier
+            // that keeps every peer from writing into it before the memset has finished
+            ok = cudaMemset(g_dist_copy, 0, DIST_HDR_BYTES) == cudaSuccess && cudaDeviceSynchronize() == cudaSuccess;
+            g_dist_copy_bytes = copy_need + DIST_HDR_BYTES;
+            }
+        if (!ok)
             cudaGetLastError();
         uint64_t hsend[9];
         export_copy(hsend);
@@ -1229,7 +1512,7 @@ int dev_reorder_distributed(uint64_t n_local, const uint32_t* keys, uint64_t out
         {
         if (p == me)
             {
-            a.peer[p] = (uint32_t*)g_dist_copy;
+            a.peer[p] = (uint32_t*)dist_inbox(g_dist_copy);
             continue;
             }
         cudaIpcMemHandle_t h;
@@ -1252,7 +1535,7 @@ int dev_reorder_distributed(uint64_t n_local, const uint32_t* keys, uint64_t out
             g_dist_peer_handle[p] = h;
             g_dist_peer_open[p] = ptr != nullptr;
             }
-        a.peer[p] = (uint32_t*)g_dist_peer[p];
+        a.peer[p] = (uint32_t*)dist_inbox(g_dist_peer[p]);
         }
     bool peers_ok = true;
     for (int p = 0; p < G; p++)
@@ -1302,6 +1585,129 @@ int dev_reorder_distributed(uint64_t n_local, const uint32_t* keys, uint64_t out
     uint32_t* lines_copy = (uint32_t*)(p8 + 256 + 2 * tb + bb + cb + 256);      // partition mode only
 
     trace.mark("peers+workspace");
+    // ---- device-driven exchange (default for > 1 rank): counts, "records delivered" and "buckets placed" travel as
+    // stores + flags between the GPUs; the host launches everything at once and reads one result at the end.
+    // PGSD_B200_DIST_HOST=1 keeps the exchange on the host communicator (3 more all-gathers, host-built tables).
+    const char* ehost = getenv("PGSD_B200_DIST_HOST");
+    if (part && !(ehost && ehost[0] == '1'))
+        {
+        const uint32_t epoch = ++g_dist_epoch;
+        const int par = (int)(epoch & 1u);
+        if (!ws_ok)
+            {
+            set_last_error("reorder_distributed: workspace allocation failed (the peers will report a timeout)");
+            return -6;
+            }
+        DistPeers peers;
+        memset(&peers, 0, sizeof(peers));
+        for (int p = 0; p < G; p++)
+            peers.shared[p] = p == me ? g_dist_copy : g_dist_peer[p];
+        uint32_t* n_owned = owner_cursor + 16;
+        uint32_t* host_out = g_slot_flag_host + 16; // pinned: [0] plan status, [1] rows owned, [2] delivery wait, [3] final wait
+        host_out[0] = host_out[1] = host_out[2] = host_out[3] = 0;
+        static bool plan_attr = false;
+        if (!plan_attr)
+            {
+            cudaFuncSetAttribute(kd_plan, cudaFuncAttributeMaxDynamicSharedMemorySize, 136 * 1024);
+            plan_attr = true;
+            }
+        cudaMemsetAsync(p8, 0, 256 + tb, st);
+        if (n_local > 0)
+            {
+            int hgrid = dev_sm_count() * (nbp <= 16384 ? 2 : 1);
+            const uint64_t want = (n_local / 4 + 1023) / 1024;
+            if ((uint64_t)hgrid > want)
+                hgrid = want ? (int)want : 1;
+            k6_slot_hist<<<hgrid, 1024, (size_t)nbp * 4, st>>>(keys, n_local, L, bmask, nbp, 0u, (uint32_t)key_limit, counts, flag);
+            dev_stats().kernel_launches++;
+            }
+        kd_publish<<<G, 256, 0, st>>>(peers, me, par, epoch, counts, nbp, flag, n_local, out_capacity, peers_ok ? 0u : (uint32_t)DST_RESOURCE);
+        kd_plan<<<1, 1024, (size_t)(nbr + 2) * 4, st>>>(g_dist_copy, G, me, par, epoch, nbp, nb_used, nbr, cap, owner_cursor, base, n_owned, flag, host_out);
+        cudaMemsetAsync(cursor, 0, (size_t)nbr * cstride * 4, st);
+        dev_stats().kernel_launches += 2;
+        cudaError_t e = cudaGetLastError();
+        SlotArgs ap = a;
+        ap.nbl = 0;
+        if (e == cudaSuccess && n_local > 0)
+            {
+            const size_t smem = ((size_t)in_words + 1) * tile * 4 + SLOT_MAX_FIELDS * SLOT_SKEW * 4 + (size_t)tile * 2;
+            const uint32_t tiles = (uint32_t)((n_local + tile - 1) / tile);
+            if (tile == 512)
+                {
+                cudaFuncSetAttribute(k6_part_scatter<512, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                k6_part_scatter<512, 128><<<tiles, 128, smem, st>>>(n_local, L, bmask, owner_cursor, flag, ap);
+                }
+            else
+                {
+                cudaFuncSetAttribute(k6_part_scatter<1024, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                k6_part_scatter<1024, 256><<<tiles, 256, smem, st>>>(n_local, L, bmask, owner_cursor, flag, ap);
+                }
+            dev_stats().kernel_launches++;
+            e = cudaGetLastError();
+            }
+        kd_signal<<<1, 32, 0, st>>>(peers, G, me, par, epoch, 0, flag);
+        kd_wait<<<1, 32, 0, st>>>(g_dist_copy, G, par, epoch, 0, flag, host_out);
+        dev_stats().kernel_launches += 2;
+        if (e == cudaSuccess && my_b1 > my_b0)
+            {
+            SlotArgs aq = a;
+            aq.bulk = 1;
+            aq.nranks = 1;
+            // my inbox (rows decided by kd_plan, any order) -> bucketed copy -> fields in id order
+            const int rt = ((size_t)a.row_words + 1) * 1024 * 4 <= 200 * 1024 ? 1024 : 512;
+            const size_t smem = ((size_t)a.row_words + 1) * rt * 4;
+            const uint32_t tiles = (uint32_t)(((uint64_t)(my_b1 - my_b0) * cap + rt - 1) / rt); // the fullest inbox possible
+            if (rt == 512)
+                {
+                cudaFuncSetAttribute(k6_slot_scatter_rec<512, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                k6_slot_scatter_rec<512, 128><<<tiles, 128, smem, st>>>((const uint32_t*)dist_inbox(g_dist_copy), 0, n_owned, L, bmask,
+                                                                       my_b0, cursor, cstride, lines_copy, flag, aq);
+                }
+            else
+                {
+                cudaFuncSetAttribute(k6_slot_scatter_rec<1024, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                k6_slot_scatter_rec<1024, 256><<<tiles, 256, smem, st>>>((const uint32_t*)dist_inbox(g_dist_copy), 0, n_owned, L, bmask,
+                                                                        my_b0, cursor, cstride, lines_copy, flag, aq);
+                }
+            k6_slot_place<<<my_b1 - my_b0, cap / 4, place_smem, st>>>(base, L, lines_copy, flag, aq);
+            dev_stats().kernel_launches += 2;
+            if (e == cudaSuccess)
+                e = cudaGetLastError();
+            }
+        kd_signal<<<1, 32, 0, st>>>(peers, G, me, par, epoch, 1, flag);
+        kd_wait<<<1, 32, 0, st>>>(g_dist_copy, G, par, epoch, 1, flag, host_out);
+        dev_stats().kernel_launches += 2;
+        if (e == cudaSuccess)
+            e = cudaGetLastError();
+        const cudaError_t es = cudaStreamSynchronize(st);
+        trace.mark("device-driven step");
+        if (e != cudaSuccess || es != cudaSuccess)
+            {
+            set_last_error(std::string("reorder_distributed: ") + cudaGetErrorString(e != cudaSuccess ? e : es));
+            cudaGetLastError();
+            return -1;
+            }
+        const uint32_t stt = host_out[0] | host_out[2] | host_out[3];
+        if (stt & DST_RESOURCE)
+            {
+            set_last_error("reorder_distributed: a rank failed to allocate or map memory, or a bulk copy did not complete");
+            return -6;
+            }
+        if (stt & DST_TIMEOUT)
+            {
+            set_last_error("reorder_distributed: a peer did not signal within the time limit");
+            return -1;
+            }
+        if (stt & DST_FITS)
+            {
+            set_last_error("reorder_distributed: out_capacity too small on some rank (rows owned: ceil(N / 2^L / ranks) * 2^L at most)");
+            return -2;
+            }
+        if (stt & (DST_RANGE | DST_OVERFLOW | DST_DUP))
+            return 1; // ids not unique / not dense: nothing of the outputs is valid, on every rank
+        *n_out = host_out[1];
+        return 0;
+        }
     // (3) local histogram, counts of all ranks
     const size_t cw = ((size_t)nbp + 1) / 2 + 1; // u64 words: packed counts + status word
     std::vector<uint64_t> csend(cw, 0), call((size_t)G * cw);
@@ -1435,9 +1841,9 @@ int dev_reorder_distributed(uint64_t n_local, const uint32_t* keys, uint64_t out
             {
             const uint32_t tiles_all = (uint32_t)((n_local + tile - 1) / tile);
             if (tile == 512)
-                e = launch_scatter<512, 128>(n_local, 0, tiles_all, L, bmask, cursor, cstride, (uint32_t*)g_dist_copy, flag, a, in_words, st);
+                e = launch_scatter<512, 128>(n_local, 0, tiles_all, L, bmask, cursor, cstride, (uint32_t*)dist_inbox(g_dist_copy), flag, a, in_words, st);
             else
-                e = launch_scatter<1024, 256>(n_local, 0, tiles_all, L, bmask, cursor, cstride, (uint32_t*)g_dist_copy, flag, a, in_words, st);
+                e = launch_scatter<1024, 256>(n_local, 0, tiles_all, L, bmask, cursor, cstride, (uint32_t*)dist_inbox(g_dist_copy), flag, a, in_words, st);
             }
         }
     cudaMemcpyAsync(g_slot_flag_host, flag, 12, cudaMemcpyDeviceToHost, st);
@@ -1469,7 +1875,7 @@ int dev_reorder_distributed(uint64_t n_local, const uint32_t* keys, uint64_t out
         SlotArgs ap = a;
         ap.bulk = 1;
         ap.nranks = 1;
-        const uint32_t* bucketed = (const uint32_t*)g_dist_copy;
+        const uint32_t* bucketed = (const uint32_t*)dist_inbox(g_dist_copy);
         if (part)
             {
             // my inbox (owned[me] records, any order) -> bucketed copy, with the cursors starting at 0
@@ -1482,13 +1888,13 @@ int dev_reorder_distributed(uint64_t n_local, const uint32_t* keys, uint64_t out
                 if (rt == 512)
                     {
                     cudaFuncSetAttribute(k6_slot_scatter_rec<512, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                    k6_slot_scatter_rec<512, 128><<<tiles, 128, smem, st>>>((const uint32_t*)g_dist_copy, owned[me], L, bmask, my_b0,
+                    k6_slot_scatter_rec<512, 128><<<tiles, 128, smem, st>>>((const uint32_t*)dist_inbox(g_dist_copy), owned[me], nullptr, L, bmask, my_b0,
                                                                            cursor, cstride, lines_copy, flag, ap);
                     }
                 else
                     {
                     cudaFuncSetAttribute(k6_slot_scatter_rec<1024, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                    k6_slot_scatter_rec<1024, 256><<<tiles, 256, smem, st>>>((const uint32_t*)g_dist_copy, owned[me], L, bmask, my_b0,
+                    k6_slot_scatter_rec<1024, 256><<<tiles, 256, smem, st>>>((const uint32_t*)dist_inbox(g_dist_copy), owned[me], nullptr, L, bmask, my_b0,
                                                                             cursor, cstride, lines_copy, flag, ap);
                     }
                 dev_stats().kernel_launches++;

@@ -110,6 +110,32 @@ cdef class _PreparedFrame:
             free(self.cols)
 
 
+cdef struct _HostChunk:
+    const char* name
+    int pgsd_type
+    uint64_t N
+    uint32_t M
+    uint64_t N_global
+    uint64_t stride
+    bint write_all
+    const void* data
+
+
+cdef class _PreparedHost:
+    """Argument table of host chunks written every frame from the same buffers (see PGSDFile.prepare_chunks)."""
+    cdef _HostChunk* chunks
+    cdef int n
+    cdef object keep
+
+    def __cinit__(self):
+        self.chunks = NULL
+        self.n = 0
+
+    def __dealloc__(self):
+        if self.chunks != NULL:
+            free(self.chunks)
+
+
 cdef class PGSDFile:
     """PGSD file access interface (ref: fl.pyx:231-380)."""
 
@@ -290,6 +316,66 @@ cdef class PGSDFile:
                 PyBuffer_Release(&buf)
         else:
             retval = self._c_write(name.encode('utf-8'), pgsd_type, N, M, N_global, stride, bool(write_all), 0, &err)
+        _raise_on_error(retval, self._name, err)
+
+    def prepare_chunks(self, chunks, rank=0):
+        """Validate a list of host chunks once and keep their ``pgsd_write_chunk`` arguments.
+
+        ``chunks``: sequence of ``(name, array, offset, write_all)`` with the meaning of :py:meth:`write_chunk`'s
+        arguments; the arrays must be C-contiguous numpy arrays with 1 or 2 dimensions.  The returned object keeps
+        the arrays alive; :py:meth:`write_prepared` writes their CURRENT contents, so a simulation that logs the
+        same scalars every step updates the arrays in place and pays the Python argument handling once instead of
+        once per chunk and frame (3.5 us each, which is most of a 4096-particle frame's cost).
+        """
+        cdef _PreparedHost ph = _PreparedHost()
+        cdef int n = len(chunks), i
+        keep = []
+        ph.chunks = <_HostChunk*>malloc(max(n, 1) * sizeof(_HostChunk))
+        if ph.chunks == NULL:
+            raise MemoryError()
+        i = 0
+        for (name, data, offset, write_all) in chunks:
+            if not isinstance(data, numpy.ndarray) or not data.flags['C_CONTIGUOUS']:
+                raise ValueError("prepare_chunks needs C-contiguous numpy arrays: " + name)
+            if data.ndim > 2:
+                raise ValueError("PGSD can only write 1 or 2 dimensional arrays: " + name)
+            N = data.shape[0] if data.ndim >= 1 else 1
+            M = data.shape[1] if data.ndim == 2 else 1
+            N_global, stride = self._offset_args(N, M, offset, rank)
+            pgsd_type = _NP_TO_PGSD.get(data.dtype)
+            if pgsd_type is None:
+                raise ValueError("invalid type for chunk: " + name)
+            bname = name.encode('utf-8')
+            keep.extend([bname, data])
+            ph.chunks[i].name = <const char*>bname
+            ph.chunks[i].pgsd_type = pgsd_type
+            ph.chunks[i].N = N
+            ph.chunks[i].M = M
+            ph.chunks[i].N_global = N_global
+            ph.chunks[i].stride = stride
+            ph.chunks[i].write_all = bool(write_all)
+            ph.chunks[i].data = <const void*><uintptr_t>(data.ctypes.data if data.size else 0)
+            i += 1
+        ph.n = n
+        ph.keep = keep
+        return ph
+
+    def write_prepared(self, _PreparedHost prepared):
+        """``pgsd_write_chunk`` for every chunk of ``prepared`` (:py:meth:`prepare_chunks`), in order, from the arrays'
+        current contents.  Equivalent to calling :py:meth:`write_chunk` for each."""
+        cdef int retval = 0, err = 0, i
+        cdef _HostChunk* c
+        cdef uint64_t gsize
+        self._check_open()
+        with nogil:
+            for i in range(prepared.n):
+                c = &prepared.chunks[i]
+                gsize = 0 if c.N_global == _AUTO else c.N_global * c.M
+                retval = libpgsd.pgsd_write_chunk(&self._handle, c.name, <libpgsd.pgsd_type>c.pgsd_type, c.N, c.M, c.N_global,
+                                                  c.M, c.stride, gsize, c.write_all, 0, c.data)
+                if retval != 0:
+                    err = errno
+                    break
         _raise_on_error(retval, self._name, err)
 
     def _write_chunk_device(self, name, data, offset, rank, write_all):

@@ -18,10 +18,12 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("nprocs,mode", [(1, "partition"), (2, "partition"), (3, "partition"), (4, "partition"), (8, "partition"),
-                                         (2, "fused"), (3, "fused"), (8, "fused")])
+                                         (2, "partition-host"), (8, "partition-host"), (2, "fused"), (3, "fused"), (8, "fused")])
 def test_reorder_distributed_equals_stable_argsort(lib, nprocs, mode):
     """mode: how records reach their owners -- "partition" (runs appended to the owner's inbox, then the local
-    two-pass reorder) or "fused" (every record stored directly at its place in the owner's bucketed copy)."""
+    two-pass reorder; counts and completion flags exchanged between the devices, default), "partition-host" (the
+    same with the exchange on the host communicator) or "fused" (every record stored directly at its place in the
+    owner's bucketed copy, host exchange)."""
     assert lib.pgsd_b200_cuda_available() == 1, "no CUDA device: the device path has no CPU fallback"
     with tempfile.TemporaryDirectory() as d:
         # a frame file for the end-to-end leg (written here by one rank: whole chunks, like any reference file)
@@ -35,7 +37,7 @@ def test_reorder_distributed_equals_stable_argsort(lib, nprocs, mode):
                 f.write_chunk(k, a)
             f.end_frame()
         seg = f"/pgsd_dist_{os.getpid()}_{nprocs}_{mode}"
-        env = dict(os.environ, PGSD_B200_DIST_MODE=mode)
+        env = dict(os.environ, PGSD_B200_DIST_MODE=mode.split("-")[0], PGSD_B200_DIST_HOST="1" if mode.endswith("-host") else "0")
         procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "dist_reorder_worker.py"), str(r), str(nprocs), seg, d],
                                   env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(nprocs)]
         outs = []

@@ -213,3 +213,32 @@ def test_communicator_cannot_be_replaced_while_files_are_open(tmp_path):
     f.end_frame()
     f.close()
     assert lib.pgsd_b200_comm_finalize() == 0
+
+
+def test_prepared_host_chunks_write_the_same_file(tmp_path):
+    """PGSDFile.prepare_chunks / write_prepared == write_chunk per chunk, with buffers updated in place."""
+    n, frames = 100, 40
+    step, box = np.zeros(1, np.uint64), np.array([10, 10, 10, 0, 0, 0], np.float32)
+    pos = np.zeros((n, 3), np.float32)
+    logs = [("log/value/v%d" % k, np.array([k], dtype=np.float32)) for k in range(3)]
+    a, b = str(tmp_path / "a.gsd"), str(tmp_path / "b.gsd")
+    with fl.open(a, 'w', 'pgsd-b200', 'hoomd', [1, 4]) as f:
+        prep = f.prepare_chunks([("configuration/step", step, None, False), ("configuration/box", box, None, False),
+                                 ("particles/position", pos, None, True)] + [(k, v, None, False) for k, v in logs])
+        for i in range(frames):
+            step[0] = 10 * i
+            pos[:] = i
+            f.write_prepared(prep)
+            f.end_frame()
+    with fl.open(b, 'w', 'pgsd-b200', 'hoomd', [1, 4]) as f:
+        for i in range(frames):
+            f.write_chunk("configuration/step", np.array([10 * i], np.uint64), write_all=False)
+            f.write_chunk("configuration/box", box, write_all=False)
+            f.write_chunk("particles/position", np.full((n, 3), i, np.float32))
+            for k, v in logs:
+                f.write_chunk(k, v, write_all=False)
+            f.end_frame()
+    assert open(a, "rb").read() == open(b, "rb").read()
+    with pytest.raises(ValueError):
+        with fl.open(a, 'w', 'pgsd-b200', 'hoomd', [1, 4]) as f:
+            f.prepare_chunks([("x", np.zeros((4, 4))[:, ::2], None, False)])
