@@ -1065,6 +1065,8 @@ def main():
     ap.add_argument("--no-vtu", action="store_true")
     ap.add_argument("--quick", action="store_true", help="skip the 14 GB benchmark-write/read legs, the disk target and the "
                                                          "config 2 / 5 legs (contract tests, development)")
+    ap.add_argument("--legs", default="", help="development: comma list of legs to run (read,dist,write,parity,disk,traj,small,bw); "
+                                                  "a partial run prints only the objects it measured")
     ap.add_argument("--only-distributed", action="store_true",
                     help="development: run only the distributed-reorder leg and print its object")
     args = ap.parse_args()
@@ -1152,6 +1154,39 @@ def main():
             dr["n_gpus"] = dist.world
             dr["clocks"] = sampler.summary(windows)
             print(json.dumps(dr), flush=True)
+        if dist.world > 1:
+            lib.pgsd_b200_comm_finalize()
+        dist.close()
+        lib.pgsd_b200_shutdown()
+        return 0
+    legs = set(x for x in args.legs.split(",") if x)
+    if legs:   # development: a subset of the legs, printed as they are
+        if dist.world > 1:
+            from pgsd_sph_b200 import comm
+            comm.init_nccl(dist.rank, dist.world, dist.bcast_bytes, dist.local)
+        out = {"n_gpus": dist.world, "partial": sorted(legs)}
+        if "read" in legs and dist.world == 1:
+            out["read_reorder"] = run_read_leg(lib, dist, args, peaks, windows)
+        if "dist" in legs:
+            out["distributed_reorder"] = run_dist_reorder_leg(lib, dist, args, peaks, windows)
+        if "write" in legs:
+            out["write"] = run_write_leg(lib, dist, args, peaks, windows)
+        if "parity" in legs:
+            out["parity"] = run_parity_leg(lib, dist, args)
+        if "disk" in legs and disk_dir():
+            out["write_disk"] = run_write_leg(lib, dist, args, peaks, windows, target_dir=disk_dir(), steps=max(2, min(args.steps, 4)),
+                                              warmup=3, legs=("device",))
+        if "traj" in legs:
+            out["trajectory_write"] = run_frames_leg(lib, dist, args, windows, TRAJ_PARTICLES, TRAJ_FRAMES, 0, "traj")
+        if "small" in legs:
+            out["small_frames"] = run_frames_leg(lib, dist, args, windows, SMALL_PARTICLES, args.small_frames, SMALL_LOGS, "small")
+        if "bw" in legs:
+            bw, bw_path = run_benchmark_write_leg(lib, dist, args, keep=True)
+            out["benchmark_write"], out["benchmark_read"] = bw, run_benchmark_read_leg(lib, dist, args, bw_path)
+        sampler.stop()
+        if dist.rank == 0:
+            out["clocks"] = sampler.summary(windows)
+            print(json.dumps(out, default=str), flush=True)
         if dist.world > 1:
             lib.pgsd_b200_comm_finalize()
         dist.close()

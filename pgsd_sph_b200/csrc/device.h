@@ -84,6 +84,9 @@ struct WriteJob
 int dev_frame_submit(int fd, const WriteJob* jobs, int njobs, void* frame);
 void dev_frame_abandon(void* frame);
 int dev_drain(); // wait for every queued file write; PGSD_ERROR_IO (-1) if one failed
+// queue a small host write behind the staged frames (copied; written in submission order by one thread); false when
+// the staging threads are not running: write synchronously then
+bool dev_async_host_write(int fd, const void* buf, uint64_t n, uint64_t off);
 int dev_copy_to_host(void* host_dst, const void* dev_src, uint64_t bytes); // synchronous
 // file -> pinned double buffer -> device (read path)
 int dev_read_file_to_device(int fd, void* dev_dst, uint64_t bytes, uint64_t file_off);

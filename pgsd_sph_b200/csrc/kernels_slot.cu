@@ -1698,13 +1698,15 @@ int dev_reorder_distributed(uint64_t n_local, const uint32_t* keys, uint64_t out
             set_last_error("reorder_distributed: a peer did not signal within the time limit");
             return -1;
             }
+        if (stt & (DST_RANGE | DST_OVERFLOW))
+            return 1; // ids not dense / more ids than slots in a bucket: not applicable, on every rank
         if (stt & DST_FITS)
             {
             set_last_error("reorder_distributed: out_capacity too small on some rank (rows owned: ceil(N / 2^L / ranks) * 2^L at most)");
             return -2;
             }
-        if (stt & (DST_RANGE | DST_OVERFLOW | DST_DUP))
-            return 1; // ids not unique / not dense: nothing of the outputs is valid, on every rank
+        if (stt & DST_DUP)
+            return 1; // two records with one id: nothing of the outputs is valid, on every rank
         *n_out = host_out[1];
         return 0;
         }

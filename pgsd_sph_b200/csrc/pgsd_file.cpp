@@ -76,6 +76,17 @@ bool pwrite_all(int fd, const void* buf, uint64_t n, uint64_t off)
     }
 
 // reads up to n bytes; returns the number read (short at end of file), -1 on error
+// The file layer's own small writes (index entries, write buffers, names, header).  While device frames are being
+// staged they are queued behind them on the staging pipeline's serial writer (one thread, submission order: see
+// device.cu) instead of contending with it for the inode lock from the caller's thread; otherwise written at once.
+// Everything queued is in the file after drain_all() (pgsd_flush, pgsd_close, reads, index relocation).
+bool put_small(int fd, const void* buf, uint64_t n, uint64_t off)
+    {
+    if (dev_async_host_write(fd, buf, n, off))
+        return true;
+    return pwrite_all(fd, buf, n, off);
+    }
+
 int64_t pread_some(int fd, void* buf, uint64_t n, uint64_t off)
     {
     char* p = (char*)buf;
@@ -488,20 +499,20 @@ int flush_name_buffer(pgsd_handle* h)
         // capacity doubled: the whole list moves to the end of the file, header is rewritten
         const uint64_t off = (uint64_t)h->file_size;
         if (h->rank == 0)
-            ok = pwrite_all(s->fd, nb.data, nb.reserved, off);
+            ok = put_small(s->fd, nb.data, nb.reserved, off);
         h->file_size += (long long)nb.reserved;
         h->header.namelist_location = off;
         h->header.namelist_allocated_entries = nb.reserved / PGSD_NAME_SIZE;
         if (h->rank == 0)
             {
-            ok = ok && pwrite_all(s->fd, &h->header, sizeof(pgsd_header), 0);
+            ok = ok && put_small(s->fd, &h->header, sizeof(pgsd_header), 0);
             dev_stats().file_bytes_written += nb.reserved + sizeof(pgsd_header);
             }
         }
     else if (h->rank == 0)
         {
         // in place: everything from the old end of the list to the end of the block
-        ok = pwrite_all(s->fd, nb.data + old_size, nb.reserved - old_size,
+        ok = put_small(s->fd, nb.data + old_size, nb.reserved - old_size,
                         h->header.namelist_location + old_size);
         dev_stats().file_bytes_written += nb.reserved - old_size;
         }
@@ -521,7 +532,7 @@ int flush_write_buffer(pgsd_handle* h)
     bool ok = true;
     if (h->write_buffer.size > 0)
         {
-        ok = pwrite_all(s->fd, h->write_buffer.data, h->write_buffer.size, base + s->wb_excl);
+        ok = put_small(s->fd, h->write_buffer.data, h->write_buffer.size, base + s->wb_excl);
         dev_stats().file_bytes_written += h->write_buffer.size;
         }
     h->file_size += (long long)s->wb_total;
@@ -617,7 +628,7 @@ int expand_file_index(pgsd_handle* h, size_t size_required)
     h->header.index_allocated_entries = size_new;
     if (h->rank == 0)
         {
-        ok = ok && pwrite_all(s->fd, &h->header, sizeof(pgsd_header), 0);
+        ok = ok && put_small(s->fd, &h->header, sizeof(pgsd_header), 0);
         dev_stats().file_bytes_written += sizeof(pgsd_header);
         }
     h->file_index.reserved = size_new;
@@ -657,7 +668,7 @@ int flush_replica(pgsd_handle* h)
     bool ok = true;
     if (h->rank == 0)
         {
-        ok = pwrite_all(s->fd, h->frame_index.data, sizeof(pgsd_index_entry) * h->frame_index.size, write_pos);
+        ok = put_small(s->fd, h->frame_index.data, sizeof(pgsd_index_entry) * h->frame_index.size, write_pos);
         dev_stats().file_bytes_written += sizeof(pgsd_index_entry) * h->frame_index.size;
         }
     size_t room = h->file_index.reserved - h->file_index.size;
