@@ -1394,10 +1394,23 @@ int dev_reorder_distributed(uint64_t n_local, const uint32_t* keys, uint64_t out
                 memcpy(w9, &h, 64);
             }
         };
-    constexpr size_t W1 = 13;
+    constexpr size_t W1 = 14;
     uint64_t mine[W1] = { n_local, out_capacity, (uint64_t)g_dist_copy_bytes };
     export_copy(mine + 3);
     mine[12] = bad_args ? 1 : 0;
+        {
+        // which physical GPU this rank runs on: ranks that SHARE a device (tests, oversubscribed hosts) must not wait
+        // for one another inside kernels -- nothing guarantees that their kernels run at the same time
+        int dev = 0;
+        cudaDeviceProp prop;
+        uint64_t h = 1469598103934665603ull;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess)
+            for (size_t i = 0; i < sizeof(prop.uuid.bytes); i++)
+                h = (h ^ (unsigned char)prop.uuid.bytes[i]) * 1099511628211ull;
+        else
+            cudaGetLastError();
+        mine[13] = h;
+        }
     std::vector<uint64_t> all((size_t)G * W1);
     if (c->allgather(mine, all.data(), W1) != 0)
         return -1;
@@ -1415,6 +1428,11 @@ int dev_reorder_distributed(uint64_t n_local, const uint32_t* keys, uint64_t out
             set_last_error("reorder_distributed: another rank was called with invalid arguments");
         return -2;
         }
+    bool shared_device = false;
+    for (int p = 0; p < G; p++)
+        for (int q = p + 1; q < G; q++)
+            if (all[(size_t)p * W1 + 13] == all[(size_t)q * W1 + 13])
+                shared_device = true;
     *n_out = 0;
     if (id_first)
         *id_first = 0;
@@ -1588,8 +1606,9 @@ int dev_reorder_distributed(uint64_t n_local, const uint32_t* keys, uint64_t out
     // ---- device-driven exchange (default for > 1 rank): counts, "records delivered" and "buckets placed" travel as
     // stores + flags between the GPUs; the host launches everything at once and reads one result at the end.
     // PGSD_B200_DIST_HOST=1 keeps the exchange on the host communicator (3 more all-gathers, host-built tables).
+    // Only with one GPU per rank: the kernels of the exchange spin on flags that the peers' kernels write.
     const char* ehost = getenv("PGSD_B200_DIST_HOST");
-    if (part && !(ehost && ehost[0] == '1'))
+    if (part && !shared_device && !(ehost && ehost[0] == '1'))
         {
         const uint32_t epoch = ++g_dist_epoch;
         const int par = (int)(epoch & 1u);

@@ -21,9 +21,11 @@ pytestmark = pytest.mark.gpu
                                          (2, "partition-host"), (8, "partition-host"), (2, "fused"), (3, "fused"), (8, "fused")])
 def test_reorder_distributed_equals_stable_argsort(lib, nprocs, mode):
     """mode: how records reach their owners -- "partition" (runs appended to the owner's inbox, then the local
-    two-pass reorder; counts and completion flags exchanged between the devices, default), "partition-host" (the
-    same with the exchange on the host communicator) or "fused" (every record stored directly at its place in the
-    owner's bucketed copy, host exchange)."""
+    two-pass reorder), "partition-host" (the same with PGSD_B200_DIST_HOST=1) or "fused" (every record stored directly
+    at its place in the owner's bucketed copy).  All ranks of this test share cuda:0, so the library keeps the
+    exchange of counts and completion flags on the host communicator in every mode (kernels of different processes
+    on one GPU must not wait for one another); the device-driven exchange runs in tests/test_gpu_multi.py, one GPU
+    per rank."""
     assert lib.pgsd_b200_cuda_available() == 1, "no CUDA device: the device path has no CPU fallback"
     with tempfile.TemporaryDirectory() as d:
         # a frame file for the end-to-end leg (written here by one rank: whole chunks, like any reference file)
