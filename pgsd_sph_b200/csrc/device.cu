@@ -207,8 +207,10 @@ bool trace_device_interval(cudaEvent_t e0, cudaEvent_t e1, double* t0_us, double
     }
 void trace_dump()
     {
-    if (!g.trace_on || g.trace_path.empty())
-        return;
+    static bool dumped = false;
+    if (!g.trace_on || g.trace_path.empty() || (dumped && g.trace.empty()))
+        return; // (shutdown and the exit hook both come here: the second call must not truncate the file)
+    dumped = true;
     FILE* f = fopen(g.trace_path.c_str(), "w");
     if (!f)
         return;

@@ -113,7 +113,19 @@ def _one_round(path, seed, nranks, mode, nthreads=4, piece=2 << 20):
     want = pattern(start, off - start)
     ok = len(got) == off and (got[:start] == 0).all() and got[start:].tobytes() == want.tobytes()
     os.unlink(path)
-    return ok
+    if ok:
+        return None
+    # describe the damage: which byte ranges differ, what is there, whose region it is
+    if len(got) != off:
+        return f"size {len(got)} != {off}"
+    diff = np.nonzero(got[start:] != want)[0] + start
+    runs = np.split(diff, np.nonzero(np.diff(diff) > 1)[0] + 1)
+    desc = []
+    for r in runs[:6]:
+        a, b = int(r[0]), int(r[-1]) + 1
+        owner = [(rk, o, nb) for rk in range(nranks) for (o, nb) in regions[rk] if o < b and a < o + nb]
+        desc.append(f"[{a},{b}) len {b - a} page_off {a % PAGE} zeros={bool((got[a:b] == 0).all())} owner(rank,off,bytes)={owner}")
+    return f"{len(diff)} bytes differ in {len(runs)} run(s): " + "; ".join(desc)
 
 
 @pytest.mark.parametrize("mode", ["mmap", "auto", "pwrite"])
@@ -123,8 +135,9 @@ def test_concurrent_ranks_and_threads_leave_the_sequential_image(tmp_path, nrank
     bad = []
     for d in targets(tmp_path):
         for i in range(iters):
-            if not _one_round(os.path.join(d, "s.bin"), 1000 * nranks + i, nranks, MODES[mode]):
-                bad.append((d, i))
+            why = _one_round(os.path.join(d, "s.bin"), 1000 * nranks + i, nranks, MODES[mode])
+            if why is not None:
+                bad.append((d, i, why))
     assert bad == [], bad
 
 
