@@ -1144,7 +1144,6 @@ int readers_init()
     {
     if (g_readers_ready)
         return 0;
-    g_read_threads = (int)default_io_threads();
     if (const char* e = getenv("PGSD_B200_READER_THREADS"))
         {
         int v = atoi(e);

@@ -103,7 +103,8 @@ bool file_write_piece(int fd, const char* p, uint64_t off, uint64_t len, bool us
     const uint64_t end = off + len;
     const uint64_t a = (off + page - 1) & ~(page - 1); // first whole page
     const uint64_t b = end & ~(page - 1);              // end of the last whole page
-    if (!use_mmap || b <= a || b - a < (1u << 20))
+    // below 256 KiB of whole pages the mapping's own cost (mmap + munmap + TLB shootdown) eats the gain
+    if (!use_mmap || b <= a || b - a < (256u << 10))
         return pwrite_range(fd, p, off, len, left);
 
     // the partial pages at either end: pwrite (their other part belongs to a neighbour who does the same)

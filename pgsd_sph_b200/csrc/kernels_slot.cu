@@ -1401,14 +1401,21 @@ int dev_reorder_distributed(uint64_t n_local, const uint32_t* keys, uint64_t out
         {
         // which physical GPU this rank runs on: ranks that SHARE a device (tests, oversubscribed hosts) must not wait
         // for one another inside kernels -- nothing guarantees that their kernels run at the same time
-        int dev = 0;
-        cudaDeviceProp prop;
-        uint64_t h = 1469598103934665603ull;
-        if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess)
-            for (size_t i = 0; i < sizeof(prop.uuid.bytes); i++)
-                h = (h ^ (unsigned char)prop.uuid.bytes[i]) * 1099511628211ull;
-        else
-            cudaGetLastError();
+        // (cudaGetDeviceProperties takes milliseconds, more with 8 processes in the driver at once: asked once)
+        static uint64_t dev_hash = 0;
+        if (dev_hash == 0)
+            {
+            int dev = 0;
+            cudaDeviceProp prop;
+            uint64_t hh = 1469598103934665603ull;
+            if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess)
+                for (size_t i = 0; i < sizeof(prop.uuid.bytes); i++)
+                    hh = (hh ^ (unsigned char)prop.uuid.bytes[i]) * 1099511628211ull;
+            else
+                cudaGetLastError();
+            dev_hash = hh | 1ull;
+            }
+        const uint64_t h = dev_hash;
         mine[13] = h;
         }
     std::vector<uint64_t> all((size_t)G * W1);
