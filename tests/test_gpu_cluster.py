@@ -1,7 +1,8 @@
-"""GPU parity tests of the cluster path of the reorder (pgsd_sph_b200/csrc/kernels_cluster.cu: coarse partition +
-cluster placement through distributed shared memory), called through the C ABI, against numpy's stable argsort +
-gather (oracle/reorder_oracle.py states the same rule).  Bit-exact.  PGSD_B200_CLUSTER_MIN_ROWS=0 sends small
-frames down the path that production only takes from 1 Mi rows on."""
+"""GPU parity tests of the cluster path of the reorder (pgsd_sph_b200/csrc/kernels_cluster.cu: coarse partition into
+write-combined runs + placement by thread-block clusters), called through the C ABI, against numpy's stable argsort
++ gather (oracle/reorder_oracle.py states the same rule).  Bit-exact.  The path is opt-in (PGSD_B200_CLUSTER=1: it
+measured slower than the slot path) and takes frames from 1 Mi rows on;
+PGSD_B200_CLUSTER_MIN_ROWS=0 sends small frames down it as well."""
 import numpy as np
 import pytest
 
@@ -22,6 +23,11 @@ def cuda(lib):
     assert lib.pgsd_b200_cuda_available() == 1, "no CUDA device: the device path has no CPU fallback"
     _lib.check(lib.pgsd_b200_device_init(0), "device_init")
     return lib
+
+
+@pytest.fixture(autouse=True)
+def cluster_on(monkeypatch):
+    monkeypatch.setenv("PGSD_B200_CLUSTER", "1")
 
 
 def _fields(n, rng):
@@ -129,7 +135,7 @@ def big_cases():
 
 @pytest.mark.parametrize("name,keys,unique", list(big_cases()), ids=[k for k, _, _ in big_cases()])
 def test_reorder_cluster_path_production_sizes(cuda, name, keys, unique):
-    """Frames of >= 1 Mi rows take the cluster path by default (no environment switches)."""
+    """Frames of >= 1 Mi rows take the cluster path once it is switched on (no other environment switches)."""
     n = len(keys)
     fields = _fields(n, np.random.default_rng(n))
     for want_perm in (False, True):

@@ -379,7 +379,7 @@ def slot_key_cases():
 def test_reorder_slot_path_equals_stable_argsort(cuda, monkeypatch, name, keys, slot, layout):
     """Unique ids take the slot path (counted by its kernel launches); duplicate ids are detected on the
     device and the stable general path produces the result.  Either way: == stable argsort + gather."""
-    monkeypatch.setenv("PGSD_B200_CLUSTER", "0")   # the cluster path (test_gpu_cluster.py) would take frames >= 1 Mi rows
+    monkeypatch.setenv("PGSD_B200_CLUSTER", "0")   # (the opt-in cluster path has its own tests: test_gpu_cluster.py)
     monkeypatch.setenv("PGSD_B200_BUCKET_MIN_ROWS", "0")
     monkeypatch.setenv("PGSD_B200_SLOT_LAYOUT", layout)
     n = len(keys)
@@ -409,7 +409,7 @@ def test_reorder_slot_path_equals_stable_argsort(cuda, monkeypatch, name, keys, 
 def test_reorder_slot_path_variants(cuda, monkeypatch, bits, tile, bulk):
     """Slot bits (bucket capacity 1024/2048/4096), scatter tile sizes, both layouts of the interleaved copy
     (128-byte lines of all buckets interleaved = default, buckets contiguous = flat), plain-load staging."""
-    monkeypatch.setenv("PGSD_B200_CLUSTER", "0")   # the cluster path (test_gpu_cluster.py) would take frames >= 1 Mi rows
+    monkeypatch.setenv("PGSD_B200_CLUSTER", "0")   # (the opt-in cluster path has its own tests: test_gpu_cluster.py)
     monkeypatch.setenv("PGSD_B200_BUCKET_MIN_ROWS", "0")
     monkeypatch.setenv("PGSD_B200_SLOT_BITS", bits)
     monkeypatch.setenv("PGSD_B200_SLOT_TILE", tile)
@@ -436,7 +436,7 @@ def test_reorder_slot_path_variants(cuda, monkeypatch, bits, tile, bulk):
 @pytest.mark.parametrize("widths", [(1,), (2, 2), (3, 3, 1, 1, 1), (4, 4, 4, 4), (5, 7), (16, 14), (16, 16)])
 def test_reorder_slot_path_row_widths(cuda, monkeypatch, widths, layout):
     """Records of 2..31 words take the slot path; wider records fall back to the general path."""
-    monkeypatch.setenv("PGSD_B200_CLUSTER", "0")   # the cluster path (test_gpu_cluster.py) would take frames >= 1 Mi rows
+    monkeypatch.setenv("PGSD_B200_CLUSTER", "0")   # (the opt-in cluster path has its own tests: test_gpu_cluster.py)
     monkeypatch.setenv("PGSD_B200_BUCKET_MIN_ROWS", "0")
     monkeypatch.setenv("PGSD_B200_SLOT_LAYOUT", layout)
     rng = np.random.default_rng(sum(widths))
@@ -461,7 +461,7 @@ def test_reorder_slot_path_random_geometry(cuda, monkeypatch, seed):
     """Seeded random cases: n, id range (10..27 bits, so every bucket count from 1 to 32768 and every slot width),
     density of the ids in that range, an id offset, record shape and whether the permutation is wanted.
     Always == numpy stable argsort + gather, bit for bit."""
-    monkeypatch.setenv("PGSD_B200_CLUSTER", "0")   # the cluster path (test_gpu_cluster.py) would take frames >= 1 Mi rows
+    monkeypatch.setenv("PGSD_B200_CLUSTER", "0")   # (the opt-in cluster path has its own tests: test_gpu_cluster.py)
     monkeypatch.setenv("PGSD_B200_BUCKET_MIN_ROWS", "0")
     rng = np.random.default_rng(9000 + seed)
     bits = int(rng.integers(10, 28))
@@ -485,7 +485,7 @@ def test_reorder_slot_path_random_geometry(cuda, monkeypatch, seed):
 
 def test_reorder_slot_path_unaligned_inputs(cuda, monkeypatch):
     """Field arrays that start 4 bytes off a 16-byte boundary are staged with plain loads."""
-    monkeypatch.setenv("PGSD_B200_CLUSTER", "0")   # the cluster path (test_gpu_cluster.py) would take frames >= 1 Mi rows
+    monkeypatch.setenv("PGSD_B200_CLUSTER", "0")   # (the opt-in cluster path has its own tests: test_gpu_cluster.py)
     monkeypatch.setenv("PGSD_B200_BUCKET_MIN_ROWS", "0")
     rng = np.random.default_rng(77)
     n = 50000
