@@ -426,8 +426,12 @@ def run_read_leg(lib, dist, args, peaks, windows):
         prep_s, enc_s = float(np.mean([a for a, _ in tv])), float(np.mean([b for _, b in tv]))
         vtu_obj = {"metric": "pgsd2vtu_Mparticles_per_s", "value": dist.world * n / (dist.max(prep_s + enc_s)) / 1e6,
                    "unit": "Mparticles/s", "prepare_s_per_frame": prep_s, "encode_write_s_per_frame": enc_s,
-                   "vtu_bytes": vbytes, "parity": "array preparation pinned vs numpy; VTU container UNPINNED (pyevtk absent, "
-                                                  "no reference output exists)"}
+                   "vtu_bytes": vbytes,
+                   "path": "file -> reordered frame in HBM -> K1 column split / f64 cast / xyz interleave -> D2H into a "
+                           "page-locked file image -> file stage (8 threads) -> .vtu",
+                   "parity": "array preparation pinned vs numpy; container laid out as pyevtk's pointsToVTK writes it "
+                             "(oracle/vtu_oracle.py, restated from its source) but UNPINNED: pyevtk is absent, the "
+                             "reference names no version and ships no output"}
     traj.close()
     os.unlink(path)
 

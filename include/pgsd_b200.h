@@ -80,7 +80,8 @@ struct pgsd_b200_column
    Replaces the host cast + contiguity copy in front of the reference's write
    (ref: fl.pyx:571 numpy.ascontiguousarray, hoomd.py:206-270 ParticleData.validate)
    followed by pgsd_write_chunk (pgsd.c:2072-2259).  Same return codes as
-   pgsd_write_chunk; unsupported casts (float -> integer) return INVALID_ARGUMENT. */
+   pgsd_write_chunk.  Every cast between the ten pgsd types is done as numpy.astype does it on x86-64
+   (float -> integer truncates toward zero). */
 int pgsd_b200_write_chunk_soa(struct pgsd_handle* handle,
                               const char* name,
                               enum pgsd_type dst_type,

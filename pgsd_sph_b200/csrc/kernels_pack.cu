@@ -206,10 +206,43 @@ __device__ __forceinline__ Wide load_wide(const void* base, long long idx, int t
     return w;
     }
 
+// float -> integer (hoomd.py:220-266 casts whatever it is given with ascontiguousarray(dtype=uint32/int32)):
+// numpy's C casts as gcc compiles them for x86-64 -- truncation toward zero.  A value whose truncation does not
+// fit (or NaN) is undefined in numpy ("invalid value encountered in cast") and differs between numpy builds
+// (scalar vs auto-vectorised loops); here it gives the conversion instruction's "integer indefinite" (the sign
+// bit alone).  Parity is claimed and tested for values that fit.  cvttsd2si r32 serves the 8/16/32-bit signed and the 8/16-bit
+// unsigned destinations, r64 serves int64; the two wide unsigned destinations go through the signed conversion
+// of x - 2^(bits-1) for x >= 2^(bits-1).  float32 sources behave as their exact float64 values.
+__device__ __forceinline__ unsigned int cvtt32(double d)
+    {
+    if (!(d < 2147483648.0) || !(d > -2147483649.0)) // NaN fails both comparisons
+        return 0x80000000u;
+    return (unsigned int)__double2int_rz(d);
+    }
+__device__ __forceinline__ unsigned long long cvtt64(double d)
+    {
+    if (!(d < 9223372036854775808.0) || !(d >= -9223372036854775808.0))
+        return 0x8000000000000000ull;
+    return (unsigned long long)__double2ll_rz(d);
+    }
+__device__ __forceinline__ unsigned long long float_to_int_bits(double d, int t)
+    {
+    switch (t)
+        {
+        case T_U32: return d >= 2147483648.0 ? (cvtt32(d - 2147483648.0) ^ 0x80000000u) : cvtt32(d);
+        case T_I64: return cvtt64(d);
+        case T_U64:
+            return d >= 9223372036854775808.0 ? (cvtt64(d - 9223372036854775808.0) ^ 0x8000000000000000ull) : cvtt64(d);
+        default: return cvtt32(d); // narrowed by the store
+        }
+    }
+
 __device__ __forceinline__ void store_wide(void* dst, unsigned long long e, int t, const Wide& w)
     {
     // integer destinations: modular narrowing of the 64-bit pattern (numpy astype wraps)
     unsigned long long bits = w.cls == 0 ? (unsigned long long)w.i : w.u;
+    if (w.cls == 2 && t != T_F32 && t != T_F64)
+        bits = float_to_int_bits(w.f, t);
     switch (t)
         {
         case T_U8:
@@ -375,8 +408,6 @@ bool cast_supported(int src, int dst)
     {
     if (type_size(src) == 0 || type_size(dst) == 0)
         return false;
-    if (is_float_type(src) && !is_float_type(dst))
-        return false; // numpy's float->int is undefined out of range; the schema never needs it
     return true;
     }
 
@@ -398,7 +429,7 @@ int pack_launch(const PackSegment* segs, int nsegs, cudaStream_t st)
         const PackSegment& g = segs[i];
         if (g.M == 0 || g.M > (unsigned)PACK_MAX_COLS || !cast_supported(g.src_type, g.dst_type))
             {
-            set_last_error("pack: unsupported segment (M must be 1..8; float->integer casts are not supported)");
+            set_last_error("pack: unsupported segment (M must be 1..8, known element types)");
             return -2;
             }
         if (g.N == 0)

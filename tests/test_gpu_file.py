@@ -184,6 +184,37 @@ def test_vtu_columns_on_device_match_numpy(golden):
         assert pd['density'].to_numpy().tobytes() == fr.particles.density.to_numpy().astype(np.float64).tobytes()
 
 
+def test_vtu_file_from_device_frame_matches_oracle(golden, tmp_path):
+    """pgsd2vtu on a device-resident reordered frame: K1 column split / f64 cast / xyz interleave, D2H into the
+    page-locked file image, threaded file stage == the sequential restatement of pyevtk's writer fed with the numpy
+    arrays of the manual's listing (container parity with pyevtk itself unpinned, see oracle/vtu_oracle.py)."""
+    from oracle import vtu_oracle
+    from pgsd_sph_b200 import vtu
+    path = os.path.join(golden, "hoomd_p2.gsd")
+    with hoomd.open(path, 'r', reorder='id', device=True) as td, hoomd.open(path, 'r', reorder='id') as th:
+        for i in (2, 0, 2):   # the second visit of frame 2 reuses the cached image
+            x, y, z, pd = vtu.point_arrays(td[i])
+            name = vtu.write_vtu(str(tmp_path / f"dev_{i}"), x, y, z, pd)
+            hx, hy, hz, hpd = vtu.point_arrays(th[i])
+            assert open(name, 'rb').read() == vtu_oracle.points_to_vtk_bytes(hx, hy, hz, hpd)
+
+
+@pytest.mark.parametrize("n", [1, 3, 100003, (1 << 21) + 7])
+def test_vtu_device_arrays_sizes(tmp_path, n):
+    """Device arrays straight into write_vtu (pointsToVTK's signature): odd sizes, > 16 MiB images (several writer
+    threads), float32 coordinates with float64 data."""
+    from oracle import vtu_oracle
+    from pgsd_sph_b200 import vtu
+    rng = np.random.default_rng(n)
+    x, y, z = (rng.standard_normal(n).astype(np.float32) for _ in range(3))
+    pd = {'rho': rng.random(n), 'v': tuple(rng.standard_normal(n) for _ in range(3)), 'k': rng.integers(0, 9, n).astype(np.uint8)}
+    dx, dy, dz = (DeviceArray.from_numpy(a) for a in (x, y, z))
+    dpd = {'rho': DeviceArray.from_numpy(pd['rho']), 'v': tuple(DeviceArray.from_numpy(a) for a in pd['v']),
+           'k': DeviceArray.from_numpy(pd['k'])}
+    name = vtu.write_vtu(str(tmp_path / "d"), dx, dy, dz, dpd)
+    assert open(name, 'rb').read() == vtu_oracle.points_to_vtk_bytes(x, y, z, pd)
+
+
 def test_torch_cuda_tensors_cai_and_dlpack(tmp_path):
     """`data` may be any CUDA array: torch tensors through __cuda_array_interface__, a DLPack-only
     wrapper through __dlpack__, a strided torch view through the device-side pack (K1)."""

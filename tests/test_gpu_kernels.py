@@ -85,21 +85,44 @@ def test_pack_f64_to_f32_special_values(cuda, N, M):
 @pytest.mark.parametrize("src", INT_TYPES + [np.float32])
 @pytest.mark.parametrize("dst", INT_TYPES + [np.float32, np.float64])
 def test_pack_cast_matrix(cuda, src, dst):
-    if np.dtype(src).kind == 'f' and np.dtype(dst).kind != 'f':
-        pytest.skip("float -> integer casts are rejected (undefined out of range in numpy)")
     rng = np.random.default_rng(np.dtype(src).num * 100 + np.dtype(dst).num)
     N, M = 3001, 3
     cols = [rand_values(rng, src, N) for _ in range(M)]
+    if np.dtype(src).kind == 'f' and np.dtype(dst).kind != 'f':
+        # float -> integer: numpy defines the cast only where the truncated value fits the destination
+        cols = [in_range_floats(rng, src, dst, N) for _ in range(M)]
     got = gpu_pack(cuda, cols, dst)
     assert got.dtype == np.dtype(dst)
     assert got.tobytes() == cast_oracle.pack_soa(cols, dst).tobytes()
 
 
-def test_pack_float_to_int_is_rejected(cuda):
-    d = DeviceArray.from_numpy(np.zeros(8, dtype=np.float32))
-    out = DeviceArray((8, 1), np.int32)
-    cols = (_lib.Column * 1)(_lib.Column(d.ptr, 1))
-    assert cuda.pgsd_b200_pack_soa(out.ptr, _lib.TYPE_INT32, 8, 1, _lib.TYPE_FLOAT, cols, None) == _lib.ERROR_INVALID_ARGUMENT
+def in_range_floats(rng, src, dst, n):
+    """Floats (fractions, both signs, the extremes) whose truncation toward zero fits dst."""
+    info = np.iinfo(dst)
+    # float32/float64 cannot hold the 64-bit extremes exactly: stay strictly inside what the source type represents
+    hi = min(float(info.max), np.nextafter(np.dtype(src).type(float(info.max) + 1.0), np.dtype(src).type(0)))
+    lo = float(info.min)
+    a = rng.uniform(max(lo, -1e18) - 0.0, min(hi, 1e18), size=n)
+    a[: n // 4] = rng.uniform(max(lo, -300.0), min(hi, 300.0), size=n // 4)  # small magnitudes with fractions
+    edge = [0.0, -0.0, 0.5, -0.5, 0.999999, -0.999999, 1.5, float(hi), float(lo), float(lo) + 0.25 if lo < 0 else 0.25]
+    a[n // 4: n // 4 + len(edge)] = edge
+    a = a.astype(src)
+    a = np.clip(a, np.dtype(src).type(lo), np.dtype(src).type(hi))
+    assert (np.trunc(a.astype(np.float64)) >= lo).all() and (np.trunc(a.astype(np.float64)) <= float(info.max)).all()
+    return a
+
+
+@pytest.mark.parametrize("src", [np.float32, np.float64])
+@pytest.mark.parametrize("dst", INT_TYPES)
+def test_pack_float_to_int_truncates_like_numpy(cuda, src, dst):
+    """hoomd.py:220-266 casts whatever it is given (ascontiguousarray(dtype=uint32/int32)): values whose truncation
+    fits the destination must give numpy's bytes.  Out-of-range values and NaN are undefined in numpy ("invalid
+    value encountered in cast") and differ between numpy builds; not tested."""
+    rng = np.random.default_rng(np.dtype(src).num * 7 + np.dtype(dst).num)
+    cols = [in_range_floats(rng, src, dst, 5003) for _ in range(2)]
+    got = gpu_pack(cuda, cols, dst)
+    assert got.dtype == np.dtype(dst)
+    assert got.tobytes() == cast_oracle.pack_soa(cols, dst).tobytes()
 
 
 @pytest.mark.parametrize("stride", [2, 4, 5])

@@ -156,8 +156,10 @@ def test_hoomd_append_defaults_and_frame0_fallback(tmp_path):
 
 
 def test_vtu_point_arrays_and_file(golden, tmp_path):
-    """pgsd2vtu input preparation == the manual's numpy.ascontiguousarray(col, float64) (pgsd.tex:1249-1259);
-    the .vtu container itself is this repository's own format choice (parity unpinned: pyevtk absent)."""
+    """pgsd2vtu input preparation == the manual's numpy.ascontiguousarray(col, float64) (pgsd.tex:1249-1259); the
+    .vtu container == the sequential restatement of pyevtk's writer in oracle/vtu_oracle.py (parity with pyevtk
+    itself UNPINNED: pyevtk is absent and the reference names no version)."""
+    from oracle import vtu_oracle
     from pgsd_sph_b200 import vtu
     with hoomd.open(os.path.join(golden, "hoomd_p2.gsd"), 'r') as t:
         fr = t[1]
@@ -167,13 +169,38 @@ def test_vtu_point_arrays_and_file(golden, tmp_path):
         assert pd['velocity'][2].tobytes() == np.ascontiguousarray(fr.particles.velocity[:, 2], dtype=np.float64).tobytes()
         assert pd['slength'].shape == (int(fr.particles.N),) and (pd['slength'] == 1).all()  # schema default (hoomd.py:178)
         name = vtu.write_vtu(str(tmp_path / "f_00001"), x, y, z, pd)
+    assert name.endswith("f_00001.vtu")
     raw = open(name, 'rb').read()
+    assert raw == vtu_oracle.points_to_vtk_bytes(x, y, z, pd)
     head, tail = raw.split(b'<AppendedData encoding="raw">\n_', 1)
     assert b'NumberOfPoints="512"' in head and b'Name="velocity" NumberOfComponents="3"' in head
     n = 512
     first = int.from_bytes(tail[:8], 'little')
     assert first == n * 3 * 8
     assert np.frombuffer(tail[8:8 + first], dtype=np.float64).reshape(n, 3)[:, 1].tobytes() == y.tobytes()
+    back = vtu_oracle.parse_vtu(raw)
+    assert back['points'][:, 2].tobytes() == z.tobytes() and back['density'].tobytes() == pd['density'].tobytes()
+    assert (back['connectivity'] == np.arange(n)).all() and (back['offsets'] == np.arange(1, n + 1)).all()
+    assert (back['types'] == 1).all() and back['velocity'][:, 0].tobytes() == pd['velocity'][0].tobytes()
+
+
+@pytest.mark.parametrize("n", [0, 1, 5, 4097, 1 << 20])
+def test_vtu_container_sizes_and_dtypes(tmp_path, n):
+    """Empty, tiny, page-straddling and multi-piece (> 16 MiB: several writer threads) files; float32 inputs, a
+    file without point data, and a second frame reusing the cached image."""
+    from oracle import vtu_oracle
+    from pgsd_sph_b200 import vtu
+    rng = np.random.default_rng(n)
+    for rep, dt in enumerate((np.float64, np.float32, np.float64)):
+        x, y, z = (rng.standard_normal(n).astype(dt) for _ in range(3))
+        pd = {'vel': tuple(rng.standard_normal(n).astype(dt) for _ in range(3)), 'rho': rng.random(n).astype(dt),
+              'tag': np.arange(n, dtype=np.int32)[::-1].copy()}
+        name = vtu.write_vtu(str(tmp_path / f"a{rep}"), x, y, z, pd)
+        assert open(name, 'rb').read() == vtu_oracle.points_to_vtk_bytes(x, y, z, pd)
+    name = vtu.write_vtu(str(tmp_path / "bare.vtu"), x, y, z)
+    assert name.endswith("bare.vtu") and open(name, 'rb').read() == vtu_oracle.points_to_vtk_bytes(x, y, z, None)
+    with pytest.raises(ValueError):
+        vtu.write_vtu(str(tmp_path / "bad"), x, y, z[:-1] if n else np.zeros(1))
 
 
 def test_reorder_distributed_plan_tiles_the_id_space():
