@@ -915,6 +915,10 @@ def run_benchmark_read_leg(lib, dist, args, path):
     for nm in names[:2]:   # warm the reader threads and pinned buffers
         f.read_chunk(0, nm, N=n, M=1, offset=start, r_all=True, device=True).free()
     lib.pgsd_b200_reset_stats()
+    import ctypes as C
+    ah0 = [C.c_uint64() for _ in range(3)]
+    lib.pgsd_b200_read_ahead_stats(*[C.byref(x) for x in ah0])
+    ah0 = [x.value for x in ah0]
     dist.barrier()
     lib.pgsd_b200_synchronize()
     t0 = time.perf_counter()
@@ -932,8 +936,15 @@ def run_benchmark_read_leg(lib, dist, args, path):
     if dist.rank == 0:
         os.unlink(path)
     gb = nkeys * nframes * n_total * 8 / 1e9
+    import ctypes as C
+    ah = [C.c_uint64() for _ in range(3)]
+    lib.pgsd_b200_read_ahead_stats(*[C.byref(x) for x in ah])
     return {"metric": "partitioned_read_GBps", "value": gb / t, "unit": "GB/s", "seconds": t,
             "h2d_bytes": int(dist.sum(float(st.h2d_bytes))),
+            "read_ahead": {"served_from_staging": ah[0].value - ah0[0], "ranges_fetched_ahead": ah[1].value - ah0[1],
+                           "fetched_never_used": ah[2].value - ah0[2],
+                           "note": "rank 0; equally sized reads at a constant file stride are fetched ahead into device "
+                                   "staging by the reader threads (PGSD_B200_READ_AHEAD=0 switches it off)"},
             "workload": "17 keys x 100 frames x 1 Mi float64 (14.26 GB), every rank reads its row slice of every key into "
                         "device memory: read_chunk(r_all=True, device=True), as benchmark-read.cc"}
 

@@ -201,6 +201,7 @@ SIGNATURES = {
     "pgsd_b200_reorder_phase_ms": (_i, [C.POINTER(C.c_float)]),
     "pgsd_b200_selftest": (_i, [_i]),
     "pgsd_b200_file_stage_write": (_i, [_i, _vp, _u64, _u64, _i]),
+    "pgsd_b200_read_ahead_stats": (_i, [C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64)]),
     "pgsd_b200_file_stage_ceiling": (_i, [C.c_char_p, _u64, _u64, C.POINTER(C.c_double), C.POINTER(_i), C.POINTER(_i)]),
 }
 

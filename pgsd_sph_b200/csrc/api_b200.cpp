@@ -391,6 +391,12 @@ int pgsd_b200_file_stage_ceiling(const char* path, uint64_t off, uint64_t bytes,
     return *seconds < 0 ? PGSD_ERROR_IO : PGSD_SUCCESS;
     }
 
+int pgsd_b200_read_ahead_stats(uint64_t* hits, uint64_t* issued, uint64_t* dropped)
+    {
+    dev_read_ahead_stats(hits, issued, dropped);
+    return PGSD_SUCCESS;
+    }
+
 int pgsd_b200_selftest(int which)
     {
     if (which == 0)

@@ -1270,8 +1270,10 @@ void read_pool_main(int t)
         }
     }
 
+void ahead_stop();
 void read_pool_stop()
     {
+    ahead_stop(); // its worker uses the pool: it goes first
     if (g_rp.th.empty())
         return;
         {
@@ -1286,14 +1288,20 @@ void read_pool_stop()
     }
     } // namespace
 
-int dev_read_file_to_device(int fd, void* dev_dst, uint64_t bytes, uint64_t file_off)
+static void read_pool_atexit()
     {
-    int rc = dev_init(-1);
-    if (rc != 0)
-        return rc;
-    if (bytes == 0)
-        return 0;
-    static std::mutex read_mu; // the reader contexts are shared: one read at a time (a prefetch thread may call us)
+    static bool hook = false;
+    if (!hook)
+        {
+        atexit(read_pool_stop);
+        hook = true;
+        }
+    }
+
+static int read_file_to_device_now(int fd, void* dev_dst, uint64_t bytes, uint64_t file_off)
+    {
+    int rc = 0;
+    static std::mutex read_mu; // the reader contexts are shared: one read at a time (read-ahead and prefetch threads call us)
     std::lock_guard<std::mutex> read_lk(read_mu);
     rc = readers_init();
     if (rc != 0)
@@ -1307,12 +1315,7 @@ int dev_read_file_to_device(int fd, void* dev_dst, uint64_t bytes, uint64_t file
         {
         if (g_rp.th.empty())
             {
-            static bool hook = false;
-            if (!hook)
-                {
-                atexit(read_pool_stop);
-                hook = true;
-                }
+            read_pool_atexit();
             for (int t = 1; t < g_read_threads; t++)
                 g_rp.th.emplace_back(read_pool_main, t);
             }
@@ -1342,6 +1345,308 @@ int dev_read_file_to_device(int fd, void* dev_dst, uint64_t bytes, uint64_t file
     g_stats.h2d_bytes += bytes;
     g_stats.file_bytes_read += bytes;
     return 0;
+    }
+
+// ---- read-ahead ------------------------------------------------------------------------------------------------------
+// A partitioned read of a trajectory is a long run of equally sized reads at a constant file stride (the reference's
+// benchmark-read: 1700 reads of 8 MiB, one per key and frame, benchmark-read.cc:46-120; a rank's row slice of one
+// field over the frames of a trajectory).  One such call costs the wake-up of the reader threads + the page-cache copy
+// + the tail of the H2D, and nothing overlaps the caller's own work between calls.  After three reads with the same
+// size and stride the next two are fetched ahead by a worker (same reader threads, same pinned pieces) into device
+// staging buffers; a call that finds its range there only pays a device-to-device copy.  Only for read-only
+// handles; every open / close of a handle drops what was fetched, and a file whose size or mtime changed is not served
+// from staging (chunks of a GSD file are never rewritten in place, so a stale range needs an outside writer that
+// replaces the file between two reads of one handle).  PGSD_B200_READ_AHEAD=0 switches it off.
+namespace
+    {
+constexpr int AHEAD_SLOTS = 3;
+constexpr uint64_t AHEAD_MIN_BYTES = 256ull << 10, AHEAD_MAX_BYTES = 64ull << 20;
+enum AheadState { AH_FREE = 0, AH_QUEUED, AH_RUNNING, AH_READY, AH_FAILED, AH_COPYING };
+struct AheadSlot
+    {
+    uint64_t off = 0, bytes = 0, cap = 0, seq = 0;
+    void* dev = nullptr;
+    int state = AH_FREE;
+    };
+struct Ahead
+    {
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    std::thread th;
+    bool running = false, stop = false;
+    int enabled = -1;
+    int fd = -1; // our own descriptor of the file being read ahead
+    dev_t dev = 0;
+    ino_t ino = 0;
+    int64_t size = 0;
+    struct timespec mtime = { 0, 0 };
+    bool have_last = false;
+    uint64_t last_off = 0, last_bytes = 0, seq = 0;
+    int64_t stride = 0;
+    int streak = 0;
+    AheadSlot slot[AHEAD_SLOTS];
+    cudaStream_t st = nullptr;
+    uint64_t hits = 0, issued = 0, dropped = 0;
+    };
+Ahead g_ah;
+
+void ahead_main()
+    {
+    cudaSetDevice(g.device);
+    for (;;)
+        {
+        AheadSlot* s = nullptr;
+        int fd = -1;
+            {
+            std::unique_lock<std::mutex> lk(g_ah.mu);
+            g_ah.cv_work.wait(lk, [&] {
+                if (g_ah.stop)
+                    return true;
+                for (AheadSlot& x : g_ah.slot)
+                    if (x.state == AH_QUEUED)
+                        return true;
+                return false;
+            });
+            if (g_ah.stop)
+                return;
+            for (AheadSlot& x : g_ah.slot)
+                if (x.state == AH_QUEUED && (s == nullptr || x.seq < s->seq))
+                    s = &x;
+            s->state = AH_RUNNING;
+            fd = g_ah.fd;
+            }
+        const bool ok = read_file_to_device_now(fd, s->dev, s->bytes, s->off) == 0;
+            {
+            std::lock_guard<std::mutex> lk(g_ah.mu);
+            s->state = ok ? AH_READY : AH_FAILED;
+            }
+        g_ah.cv_done.notify_all();
+        }
+    }
+
+// forget the file: nothing queued, nothing running, descriptor closed (buffers stay for the next file)
+void ahead_forget(std::unique_lock<std::mutex>& lk)
+    {
+    for (AheadSlot& x : g_ah.slot)
+        if (x.state == AH_QUEUED)
+            x.state = AH_FREE;
+    g_ah.cv_done.wait(lk, [] {
+        for (AheadSlot& x : g_ah.slot)
+            if (x.state == AH_RUNNING || x.state == AH_COPYING)
+                return false;
+        return true;
+    });
+    for (AheadSlot& x : g_ah.slot)
+        {
+        if (x.state == AH_READY)
+            g_ah.dropped++;
+        x.state = AH_FREE;
+        }
+    if (g_ah.fd >= 0)
+        close(g_ah.fd);
+    g_ah.fd = -1;
+    g_ah.have_last = false;
+    g_ah.streak = 0;
+    }
+
+void ahead_stop()
+    {
+        {
+        std::unique_lock<std::mutex> lk(g_ah.mu);
+        if (!g_ah.running && g_ah.fd < 0 && g_ah.slot[0].dev == nullptr)
+            return;
+        ahead_forget(lk);
+        g_ah.stop = true;
+        }
+    g_ah.cv_work.notify_all();
+    if (g_ah.running)
+        g_ah.th.join();
+    std::lock_guard<std::mutex> lk(g_ah.mu);
+    g_ah.running = false;
+    g_ah.stop = false;
+    for (AheadSlot& x : g_ah.slot)
+        {
+        if (x.dev)
+            cudaFree(x.dev);
+        x = AheadSlot();
+        }
+    if (g_ah.st)
+        cudaStreamDestroy(g_ah.st);
+    g_ah.st = nullptr;
+    }
+
+bool ahead_same_file(const struct stat& st)
+    {
+    return g_ah.fd >= 0 && st.st_dev == g_ah.dev && st.st_ino == g_ah.ino && (int64_t)st.st_size == g_ah.size
+           && st.st_mtim.tv_sec == g_ah.mtime.tv_sec && st.st_mtim.tv_nsec == g_ah.mtime.tv_nsec;
+    }
+    } // namespace
+
+void dev_read_ahead_reset()
+    {
+    std::unique_lock<std::mutex> lk(g_ah.mu);
+    if (g_ah.fd >= 0)
+        ahead_forget(lk);
+    }
+
+void dev_read_ahead_stats(uint64_t* hits, uint64_t* issued, uint64_t* dropped)
+    {
+    std::lock_guard<std::mutex> lk(g_ah.mu);
+    if (hits)
+        *hits = g_ah.hits;
+    if (issued)
+        *issued = g_ah.issued;
+    if (dropped)
+        *dropped = g_ah.dropped;
+    }
+
+int dev_read_file_to_device(int fd, void* dev_dst, uint64_t bytes, uint64_t file_off, bool read_only)
+    {
+    int rc = dev_init(-1);
+    if (rc != 0)
+        return rc;
+    if (bytes == 0)
+        return 0;
+    if (g_ah.enabled < 0)
+        {
+        const char* e = getenv("PGSD_B200_READ_AHEAD");
+        g_ah.enabled = (e && e[0] == '0') ? 0 : 1;
+        }
+    struct stat st;
+    if (!read_only || !g_ah.enabled || bytes < AHEAD_MIN_BYTES || bytes > AHEAD_MAX_BYTES || fstat(fd, &st) != 0)
+        return read_file_to_device_now(fd, dev_dst, bytes, file_off);
+
+    bool served = false;
+        {
+        std::unique_lock<std::mutex> lk(g_ah.mu);
+        if (!ahead_same_file(st))
+            {
+            ahead_forget(lk);
+            g_ah.fd = dup(fd);
+            g_ah.dev = st.st_dev;
+            g_ah.ino = st.st_ino;
+            g_ah.size = (int64_t)st.st_size;
+            g_ah.mtime = st.st_mtim;
+            }
+        // (1) fetched ahead?
+        AheadSlot* hit = nullptr;
+        for (AheadSlot& x : g_ah.slot)
+            if ((x.state == AH_QUEUED || x.state == AH_RUNNING || x.state == AH_READY) && x.off == file_off && x.bytes == bytes)
+                hit = &x;
+        if (hit)
+            {
+            g_ah.cv_done.wait(lk, [&] { return hit->state == AH_READY || hit->state == AH_FAILED; });
+            if (hit->state == AH_READY)
+                {
+                if (g_ah.st == nullptr && cudaStreamCreateWithFlags(&g_ah.st, cudaStreamNonBlocking) != cudaSuccess)
+                    g_ah.st = nullptr;
+                hit->state = AH_COPYING; // nobody else matches or recycles it meanwhile
+                lk.unlock();
+                served = g_ah.st != nullptr
+                         && cudaMemcpyAsync(dev_dst, hit->dev, bytes, cudaMemcpyDeviceToDevice, g_ah.st) == cudaSuccess
+                         && cudaStreamSynchronize(g_ah.st) == cudaSuccess;
+                if (!served)
+                    cudaGetLastError();
+                lk.lock();
+                if (served)
+                    g_ah.hits++;
+                }
+            hit->state = AH_FREE;
+            g_ah.cv_done.notify_all();
+            }
+        // (2) the pattern: same size, same stride
+        if (g_ah.have_last && bytes == g_ah.last_bytes)
+            {
+            const int64_t d = (int64_t)file_off - (int64_t)g_ah.last_off;
+            if (d == g_ah.stride && d != 0)
+                g_ah.streak++;
+            else
+                {
+                g_ah.stride = d;
+                g_ah.streak = d != 0 ? 1 : 0;
+                }
+            }
+        else
+            {
+            g_ah.stride = 0;
+            g_ah.streak = 0;
+            }
+        g_ah.have_last = true;
+        g_ah.last_off = file_off;
+        g_ah.last_bytes = bytes;
+        // (3) what should be in flight now: the next two ranges of the pattern; everything else is dropped
+        uint64_t want[2] = { 0, 0 };
+        int nwant = 0;
+        if (g_ah.streak >= 2 && g_ah.fd >= 0)
+            for (int k = 1; k <= 2; k++)
+                {
+                const int64_t t = (int64_t)file_off + k * g_ah.stride;
+                if (t < 0 || (uint64_t)t + bytes > (uint64_t)g_ah.size)
+                    break;
+                want[nwant++] = (uint64_t)t;
+                }
+        for (AheadSlot& x : g_ah.slot)
+            {
+            if (x.state == AH_FREE || x.state == AH_RUNNING || x.state == AH_COPYING)
+                continue;
+            bool wanted = false;
+            for (int k = 0; k < nwant; k++)
+                wanted = wanted || (x.off == want[k] && x.bytes == bytes);
+            if (!wanted || x.state == AH_FAILED)
+                {
+                if (x.state == AH_READY)
+                    g_ah.dropped++;
+                x.state = AH_FREE;
+                }
+            }
+        bool queued = false;
+        for (int k = 0; k < nwant; k++)
+            {
+            bool have = false;
+            for (AheadSlot& x : g_ah.slot)
+                have = have || (x.state != AH_FREE && x.off == want[k] && x.bytes == bytes);
+            if (have)
+                continue;
+            AheadSlot* f = nullptr;
+            for (AheadSlot& x : g_ah.slot)
+                if (x.state == AH_FREE && f == nullptr)
+                    f = &x;
+            if (f == nullptr)
+                break;
+            if (f->cap < bytes)
+                {
+                if (f->dev)
+                    cudaFree(f->dev);
+                f->dev = nullptr;
+                f->cap = 0;
+                if (cudaMalloc(&f->dev, bytes) != cudaSuccess)
+                    {
+                    cudaGetLastError();
+                    break;
+                    }
+                f->cap = bytes;
+                }
+            f->off = want[k];
+            f->bytes = bytes;
+            f->seq = ++g_ah.seq;
+            f->state = AH_QUEUED;
+            g_ah.issued++;
+            queued = true;
+            }
+        if (queued)
+            {
+            if (!g_ah.running)
+                {
+                read_pool_atexit();
+                g_ah.th = std::thread(ahead_main);
+                g_ah.running = true;
+                }
+            g_ah.cv_work.notify_one();
+            }
+        }
+    if (served)
+        return 0;
+    return read_file_to_device_now(fd, dev_dst, bytes, file_off);
     }
 
 // ------------------------------------------------------------------------------ K2

@@ -89,7 +89,10 @@ int dev_drain(); // wait for every queued file write; PGSD_ERROR_IO (-1) if one 
 bool dev_async_host_write(int fd, const void* buf, uint64_t n, uint64_t off);
 int dev_copy_to_host(void* host_dst, const void* dev_src, uint64_t bytes); // synchronous
 // file -> pinned double buffer -> device (read path)
-int dev_read_file_to_device(int fd, void* dev_dst, uint64_t bytes, uint64_t file_off);
+// read_only: the handle cannot write -- equally sized reads at a constant stride are fetched ahead (device.cu)
+int dev_read_file_to_device(int fd, void* dev_dst, uint64_t bytes, uint64_t file_off, bool read_only);
+void dev_read_ahead_reset(); // drop what was fetched ahead (every open / close of a handle)
+void dev_read_ahead_stats(uint64_t* hits, uint64_t* issued, uint64_t* dropped);
 
 // ---- K1 alone (no arena, no file)
 int dev_pack(void* dst_dev, int dst_type, uint64_t N, uint32_t M, int src_type, const Column* cols,

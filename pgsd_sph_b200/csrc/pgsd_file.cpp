@@ -910,7 +910,7 @@ int file_write_chunk_device(pgsd_handle* h, const char* name, int dst_type, uint
 
 int file_read_to_device(pgsd_handle* h, void* dev_dst, uint64_t bytes, uint64_t file_off)
     {
-    return dev_read_file_to_device(state_of(h)->fd, dev_dst, bytes, file_off);
+    return dev_read_file_to_device(state_of(h)->fd, dev_dst, bytes, file_off, h->open_flags == PGSD_OPEN_READONLY);
     }
 } // namespace pgsdb
 
@@ -933,6 +933,7 @@ int pgsd_create_and_open(struct pgsd_handle* handle, const char* fname, const ch
     if (handle == nullptr || fname == nullptr || application == nullptr || schema == nullptr)
         return PGSD_ERROR_INVALID_ARGUMENT;
     memset(handle, 0, sizeof(*handle));
+    dev_read_ahead_reset(); // ranges fetched ahead for a read-only handle may belong to the file replaced here
     if (flags == PGSD_OPEN_READONLY)
         return PGSD_ERROR_FILE_MUST_BE_WRITABLE;
     if (flags == PGSD_OPEN_READWRITE || flags == PGSD_OPEN_APPEND)
@@ -996,6 +997,7 @@ int pgsd_open(struct pgsd_handle* handle, const char* fname, enum pgsd_open_flag
     if (flags != PGSD_OPEN_READWRITE && flags != PGSD_OPEN_READONLY && flags != PGSD_OPEN_APPEND)
         return PGSD_ERROR_IO; // the reference opens nothing for an unknown flag and fails on fh == NULL
     handle->open_flags = flags;
+    dev_read_ahead_reset();
     FileState* s = new FileState;
     s->comm = comm();
     comm_acquire();
@@ -1024,6 +1026,7 @@ int pgsd_close(struct pgsd_handle* handle)
         if (rc != PGSD_SUCCESS)
             return rc;
         }
+    dev_read_ahead_reset();
     FileState* s = state_of(handle);
     int fd = s->fd;
     s->fd = -1;
@@ -1183,7 +1186,7 @@ int pgsd_read_chunk(struct pgsd_handle* handle, void* data, const struct pgsd_in
         return PGSD_ERROR_FILE_CORRUPT;
     FileState* s = state_of(handle);
     if (dev_is_device_pointer(data))
-        return dev_read_file_to_device(s->fd, data, size, (uint64_t)e.location + stride);
+        return dev_read_file_to_device(s->fd, data, size, (uint64_t)e.location + stride, handle->open_flags == PGSD_OPEN_READONLY);
     int64_t got = pread_some(s->fd, data, size, (uint64_t)e.location + stride);
     if (got < 0)
         return PGSD_ERROR_IO;

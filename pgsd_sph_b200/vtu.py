@@ -5,8 +5,8 @@ The reference ships this converter only as a listing in its manual
 splits position / velocity into columns, casts every array to contiguous float64 and hands them to
 ``pyevtk.hl.pointsToVTK(path, x, y, z, pointData)``.  pyevtk is a third-party module that the reference
 neither pins nor vendors and that is not installed here.  :func:`write_vtu` takes the same arguments and
-lays the file out the way pyevtk's writer does (as restated in oracle/vtu_oracle.py from its published
-source: VTK XML UnstructuredGrid of vertex cells, Int32 connectivity / offsets, UInt8 types, appended raw
+lays the file out the way pyevtk's writer does (restated call by call in the test suite's VTU checker from its
+published source: VTK XML UnstructuredGrid of vertex cells, Int32 connectivity / offsets, UInt8 types, appended raw
 data with UInt64 block sizes, x/y/z interleaved), but no pyevtk output exists to compare with --
 CONTAINER PARITY UNPINNED.  What is pinned is the array preparation (:func:`point_arrays`): it must equal
 the listing's ``numpy.ascontiguousarray(col, dtype=numpy.float64)`` bit for bit.
