@@ -1129,14 +1129,21 @@ int dev_copy_to_host(void* host_dst, const void* dev_src, uint64_t bytes)
 namespace
     {
 constexpr uint64_t READ_PIECE = 1ull << 20; // small pieces: the pipeline of a read fills in ~0.3 ms
+// Reads of a few MiB (one chunk of a 1 Mi-row field; the reference's benchmark-read issues 1700 of 8 MiB) would give
+// every reader thread ONE 1-MiB piece: all page-cache copies first, all H2D copies after them (8 MiB over PCIe is
+// 0.16 ms -- 40 % on top of the copies).  Such reads are cut into 256-KiB pieces, 8 buffers per thread, so the DMA of a
+// thread's first piece runs while it copies its second.
+constexpr uint64_t READ_PIECE_SMALL = 256ull << 10, READ_SMALL_BELOW = 32ull << 20;
+constexpr int READ_BUFS_MAX = (int)(2 * READ_PIECE / READ_PIECE_SMALL);
 constexpr int READ_THREADS_MAX = 32;
 int g_read_threads = 8; // PGSD_B200_READER_THREADS (file -> pinned saturates near 35 GB/s from 6 threads up)
 struct Reader
     {
-    char* buf[2] = { nullptr, nullptr };
-    cudaEvent_t ev[2] = { nullptr, nullptr };
+    char* buf = nullptr; // 2 * READ_PIECE bytes, page-locked: 2 large or 8 small piece buffers
+    cudaEvent_t ev[READ_BUFS_MAX] = { nullptr };
     cudaStream_t st = nullptr;
     };
+inline uint64_t read_piece_for(uint64_t bytes) { return bytes < READ_SMALL_BELOW ? READ_PIECE_SMALL : READ_PIECE; }
 Reader g_readers[READ_THREADS_MAX];
 bool g_readers_ready = false;
 
@@ -1154,11 +1161,9 @@ int readers_init()
         {
         Reader& r = g_readers[i];
         CUDA_TRY(cudaStreamCreateWithFlags(&r.st, cudaStreamNonBlocking), -1);
-        for (int k = 0; k < 2; k++)
-            {
-            CUDA_TRY(cudaHostAlloc((void**)&r.buf[k], READ_PIECE, cudaHostAllocDefault), -6);
+        CUDA_TRY(cudaHostAlloc((void**)&r.buf, 2 * READ_PIECE, cudaHostAllocDefault), -6);
+        for (int k = 0; k < READ_BUFS_MAX; k++)
             CUDA_TRY(cudaEventCreateWithFlags(&r.ev[k], cudaEventDisableTiming), -1);
-            }
         }
     g_readers_ready = true;
     return 0;
@@ -1171,13 +1176,13 @@ void readers_release()
     for (int i = 0; i < READ_THREADS_MAX; i++)
         {
         Reader& r = g_readers[i];
-        for (int k = 0; k < 2; k++)
+        if (r.buf)
+            cudaFreeHost(r.buf);
+        r.buf = nullptr;
+        for (int k = 0; k < READ_BUFS_MAX; k++)
             {
-            if (r.buf[k])
-                cudaFreeHost(r.buf[k]);
             if (r.ev[k])
                 cudaEventDestroy(r.ev[k]);
-            r.buf[k] = nullptr;
             r.ev[k] = nullptr;
             }
         if (r.st)
@@ -1192,18 +1197,21 @@ bool reader_run(int t, int T, int fd, char* dev_dst, uint64_t bytes, uint64_t fi
     {
     cudaSetDevice(g.device);
     Reader& r = g_readers[t];
-    const uint64_t npieces = (bytes + READ_PIECE - 1) / READ_PIECE;
+    const uint64_t piece = read_piece_for(bytes);
+    const int nbuf = (int)(2 * READ_PIECE / piece);
+    const uint64_t npieces = (bytes + piece - 1) / piece;
     int k = 0;
     bool ok = true;
     for (uint64_t i = (uint64_t)t; ok && i < npieces; i += (uint64_t)T)
         {
-        const uint64_t off = i * READ_PIECE;
-        const uint64_t len = bytes - off < READ_PIECE ? bytes - off : READ_PIECE;
-        ok = cudaEventSynchronize(r.ev[k]) == cudaSuccess;
+        const uint64_t off = i * piece;
+        const uint64_t len = bytes - off < piece ? bytes - off : piece;
+        char* const buf = r.buf + (uint64_t)k * piece;
+        ok = cudaEventSynchronize(r.ev[k]) == cudaSuccess; // the copy that last used this buffer is done
         uint64_t got = 0;
         while (ok && got < len)
             {
-            ssize_t n = pread(fd, r.buf[k] + got, len - got, (off_t)(file_off + off + got));
+            ssize_t n = pread(fd, buf + got, len - got, (off_t)(file_off + off + got));
             if (n < 0 && errno == EINTR)
                 continue;
             if (n <= 0)
@@ -1211,9 +1219,9 @@ bool reader_run(int t, int T, int fd, char* dev_dst, uint64_t bytes, uint64_t fi
             else
                 got += (uint64_t)n;
             }
-        ok = ok && cudaMemcpyAsync(dev_dst + off, r.buf[k], len, cudaMemcpyHostToDevice, r.st) == cudaSuccess
+        ok = ok && cudaMemcpyAsync(dev_dst + off, buf, len, cudaMemcpyHostToDevice, r.st) == cudaSuccess
              && cudaEventRecord(r.ev[k], r.st) == cudaSuccess;
-        k ^= 1;
+        k = k + 1 == nbuf ? 0 : k + 1;
         }
     return cudaStreamSynchronize(r.st) == cudaSuccess && ok;
     }
@@ -1306,7 +1314,8 @@ static int read_file_to_device_now(int fd, void* dev_dst, uint64_t bytes, uint64
     rc = readers_init();
     if (rc != 0)
         return rc;
-    const uint64_t npieces = (bytes + READ_PIECE - 1) / READ_PIECE;
+    const uint64_t piece = read_piece_for(bytes);
+    const uint64_t npieces = (bytes + piece - 1) / piece;
     const int T = npieces < (uint64_t)g_read_threads ? (int)npieces : g_read_threads;
     bool ok = true;
     if (T == 1)
