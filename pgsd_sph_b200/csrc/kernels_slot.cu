@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(1024) k6_slot_scan(const uint32_t* __restrict_
 // are in flight while the TMA engine brings the payload tiles.
 
 template <int T, int NT>
-__global__ void __launch_bounds__(NT) k6_slot_scatter(uint64_t n, uint32_t tile_first, int L, uint32_t bmask, uint32_t* __restrict__ cursor,
+__global__ void __launch_bounds__(NT, (2048 / NT > 8 ? 8 : 2048 / NT)) k6_slot_scatter(uint64_t n, uint32_t tile_first, int L, uint32_t bmask, uint32_t* __restrict__ cursor,
                                                      uint32_t cstride, uint32_t* __restrict__ aos, uint32_t* __restrict__ flag,
                                                      const __grid_constant__ SlotArgs args)
     {
@@ -277,7 +277,8 @@ __global__ void __launch_bounds__(NT) k6_slot_scatter(uint64_t n, uint32_t tile_
             }
         }
 
-    // (2) one position per row from the bucket's cursor
+    // (2) one position per row from the bucket's cursor.  (Issuing all of a thread's atomics before the first result is
+    // used was measured slower: 0.53 instead of 0.49 ms at 4 rows per thread, no difference at 2 -- profiles/r4_ab_slot.txt.)
     uint32_t d[PER];
 #pragma unroll
     for (int k = 0; k < PER; k++)
@@ -1007,13 +1008,25 @@ static cudaError_t launch_scatter(uint64_t n, uint32_t tile_first, uint32_t tile
                                   uint32_t cstride, uint32_t* aos, uint32_t* flag, const SlotArgs& a, uint32_t in_words,
                                   cudaStream_t st)
     {
-    const size_t smem = ((size_t)in_words + 1) * T * 4 + SLOT_MAX_FIELDS * SLOT_SKEW * 4;
+    // Shared-memory carve-out in KB (PGSD_B200_SLOT_CARVEOUT, read once; default 196).  With 4 CTAs of 46.5 KB the driver
+    // picks 200 KB on its own, but as soon as a fifth CTA would fit it takes 228 KB, and the L1 that is left is too
+    // small for the stores and atomics in flight: scatter 0.56 instead of 0.45 ms (profiles/r4_ab_slot2.txt).
+    static int carve = -1;
+    if (carve < 0)
+        {
+        const char* e = getenv("PGSD_B200_SLOT_CARVEOUT");
+        carve = e ? atoi(e) : 196;
+        }
+    // field tiles (+ skew behind every one) + the row -> position table
+    const size_t smem = ((size_t)in_words + 1) * T * 4 + (size_t)(a.nfields + 1) * SLOT_SKEW * 4;
     static size_t attr = 0;
     if (smem > attr)
         {
         cudaError_t e = cudaFuncSetAttribute(k6_slot_scatter<T, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess)
             return e;
+        if (carve > 0)
+            cudaFuncSetAttribute(k6_slot_scatter<T, NT>, cudaFuncAttributePreferredSharedMemoryCarveout, carve * 100 / 228);
         attr = smem;
         }
     if (tiles == 0)
@@ -1117,6 +1130,12 @@ int dev_reorder_slot(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, ui
         tile = 1024;
     while (tile > 512 && ((size_t)in_words + 1) * tile * 4 > 200 * 1024)
         tile /= 2;
+    // rows per thread of the scatter (tile / threads): fewer rows = more warps per SM for the same shared memory
+    int per = 2; // 512 threads for a 1024-row tile: 4 CTAs = 64 warps per SM (0.445 ms; 4 rows per thread: 0.49 ms)
+    if (const char* ep = getenv("PGSD_B200_SLOT_PER"))
+        per = atoi(ep);
+    if (per != 1 && per != 2 && per != 4)
+        per = 2;
     if (((size_t)in_words + 1) * tile * 4 > 200 * 1024)
         return 0;
 
@@ -1191,15 +1210,21 @@ int dev_reorder_slot(uint64_t n, const uint32_t* keys, uint32_t* keys_sorted, ui
     k6_slot_scan<<<1, 1024, (size_t)(nb + nb / 32 + 1) * 4, st>>>(counts, nb, cap, (uint32_t)n, base, lines ? nullptr : cursor, cstride, flag);
     dev_stats().kernel_launches += 2;
     cudaError_t e = cudaGetLastError();
-    const uint32_t tiles_all = (uint32_t)((n + tile - 1) / tile);
-    if (e == cudaSuccess)
+    const uint32_t tiles_all = (uint32_t)((n + tile - 1) / tile), tile_first = 0;
+    if (e == cudaSuccess && tiles_all > 0)
         {
         if (tile == 512)
-            e = launch_scatter<512, 128>(n, 0, tiles_all, L, bmask, cursor, cstride, aos, flag, a, in_words, st);
+            e = per == 2 ? launch_scatter<512, 256>(n, tile_first, tiles_all, L, bmask, cursor, cstride, aos, flag, a, in_words, st)
+                         : launch_scatter<512, 128>(n, tile_first, tiles_all, L, bmask, cursor, cstride, aos, flag, a, in_words, st);
         else if (tile == 2048)
-            e = launch_scatter<2048, 512>(n, 0, tiles_all, L, bmask, cursor, cstride, aos, flag, a, in_words, st);
+            e = per == 2 ? launch_scatter<2048, 1024>(n, tile_first, tiles_all, L, bmask, cursor, cstride, aos, flag, a, in_words, st)
+                         : launch_scatter<2048, 512>(n, tile_first, tiles_all, L, bmask, cursor, cstride, aos, flag, a, in_words, st);
+        else if (per == 1)
+            e = launch_scatter<1024, 1024>(n, tile_first, tiles_all, L, bmask, cursor, cstride, aos, flag, a, in_words, st);
+        else if (per == 2)
+            e = launch_scatter<1024, 512>(n, tile_first, tiles_all, L, bmask, cursor, cstride, aos, flag, a, in_words, st);
         else
-            e = launch_scatter<1024, 256>(n, 0, tiles_all, L, bmask, cursor, cstride, aos, flag, a, in_words, st);
+            e = launch_scatter<1024, 256>(n, tile_first, tiles_all, L, bmask, cursor, cstride, aos, flag, a, in_words, st);
         }
     if (mark)
         mark(0, st);
@@ -1869,9 +1894,9 @@ int dev_reorder_distributed(uint64_t n_local, const uint32_t* keys, uint64_t out
             {
             const uint32_t tiles_all = (uint32_t)((n_local + tile - 1) / tile);
             if (tile == 512)
-                e = launch_scatter<512, 128>(n_local, 0, tiles_all, L, bmask, cursor, cstride, (uint32_t*)dist_inbox(g_dist_copy), flag, a, in_words, st);
+                e = launch_scatter<512, 256>(n_local, 0, tiles_all, L, bmask, cursor, cstride, (uint32_t*)dist_inbox(g_dist_copy), flag, a, in_words, st);
             else
-                e = launch_scatter<1024, 256>(n_local, 0, tiles_all, L, bmask, cursor, cstride, (uint32_t*)dist_inbox(g_dist_copy), flag, a, in_words, st);
+                e = launch_scatter<1024, 512>(n_local, 0, tiles_all, L, bmask, cursor, cstride, (uint32_t*)dist_inbox(g_dist_copy), flag, a, in_words, st);
             }
         }
     cudaMemcpyAsync(g_slot_flag_host, flag, 12, cudaMemcpyDeviceToHost, st);

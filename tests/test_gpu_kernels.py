@@ -455,6 +455,58 @@ def test_reorder_slot_path_variants(cuda, monkeypatch, bits, tile, bulk):
         assert g.tobytes() == f[o].tobytes()
 
 
+@pytest.mark.parametrize("n", [1024, 1025, 2047, 5 * 1024, 100003, (1 << 20) + 77, 3 << 20])
+def test_reorder_slot_sph_row(cuda, monkeypatch, n):
+    """The 40-byte SPH row (key + position + velocity + three scalars) without the original-index column -- the call
+    pgsd.hoomd makes -- at sizes around the tile boundaries: stable-argsort order bit for bit; ids with gaps and a
+    duplicate (-> general path) included."""
+    monkeypatch.setenv("PGSD_B200_CLUSTER", "0")
+    monkeypatch.setenv("PGSD_B200_BUCKET_MIN_ROWS", "0")
+    rng = np.random.default_rng(n)
+    for case in ("dense", "gaps", "duplicate"):
+        if case == "dense":
+            keys = rng.permutation(n).astype(np.uint32)
+        elif case == "gaps":
+            keys = rng.permutation(n + n // 7 + 3)[:n].astype(np.uint32)
+        else:
+            keys = rng.permutation(n).astype(np.uint32)
+            keys[n // 2] = keys[n // 3]
+        fields = [rng.standard_normal((n, 3)).astype(np.float32), rng.standard_normal((n, 3)).astype(np.float32),
+                  rng.standard_normal(n).astype(np.float32), rng.standard_normal(n).astype(np.float32),
+                  rng.integers(0, 2 ** 32, size=n, dtype=np.uint64).astype(np.uint32)]
+        o = np.argsort(keys, kind='stable')
+        s, p, outs = _reorder_device_full(cuda, keys, fields, False)
+        assert (s == keys[o]).all()
+        for f, g in zip(fields, outs):
+            assert g.tobytes() == f[o].tobytes(), case
+
+
+@pytest.mark.parametrize("layout", ["flat", "lines"])
+@pytest.mark.parametrize("tile", ["512", "1024", "2048"])
+@pytest.mark.parametrize("per", ["1", "2", "4"])
+def test_reorder_slot_scatter_rows_per_thread(cuda, monkeypatch, per, tile, layout):
+    """Scatter launch shapes: 1, 2 or 4 rows per thread (PGSD_B200_SLOT_PER) for every tile size, with and without
+    the original-index column, sizes that leave a ragged last tile."""
+    monkeypatch.setenv("PGSD_B200_CLUSTER", "0")
+    monkeypatch.setenv("PGSD_B200_BUCKET_MIN_ROWS", "0")
+    monkeypatch.setenv("PGSD_B200_SLOT_PER", per)
+    monkeypatch.setenv("PGSD_B200_SLOT_TILE", tile)
+    monkeypatch.setenv("PGSD_B200_SLOT_LAYOUT", layout)
+    for n in (1023, 4096, 300007):
+        rng = np.random.default_rng(n + int(per) + int(tile))
+        keys = rng.permutation(n).astype(np.uint32)
+        fields = [rng.standard_normal((n, 3)).astype(np.float32), rng.standard_normal((n, 3)).astype(np.float32),
+                  rng.standard_normal(n).astype(np.float32), rng.integers(0, 2 ** 32, size=n, dtype=np.uint64).astype(np.uint32)]
+        o = np.argsort(keys, kind='stable')
+        for want_perm in (True, False):
+            cuda.pgsd_b200_reset_stats()
+            s, p, outs = _reorder_device_full(cuda, keys, fields, want_perm)
+            assert _launches(cuda) in SLOT_LAUNCHES
+            assert (s == keys[o]).all() and (p is None or (p == o.astype(np.uint32)).all())
+            for f, g in zip(fields, outs):
+                assert g.tobytes() == f[o].tobytes()
+
+
 @pytest.mark.parametrize("layout", ["flat", "lines"])
 @pytest.mark.parametrize("widths", [(1,), (2, 2), (3, 3, 1, 1, 1), (4, 4, 4, 4), (5, 7), (16, 14), (16, 16)])
 def test_reorder_slot_path_row_widths(cuda, monkeypatch, widths, layout):

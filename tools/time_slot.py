@@ -10,12 +10,18 @@ from pgsd_sph_b200.devmem import DeviceArray
 lib = _lib.load(); _lib.check(lib.pgsd_b200_device_init(0), "init")
 PEAK = 6546.6
 t = C.c_void_p(); lib.pgsd_b200_timer_create(C.byref(t))
-KNOBS = ["PGSD_B200_SLOT_UNIT", "PGSD_B200_SLOT_LAYOUT", "PGSD_B200_SLOT_CSTRIDE", "PGSD_B200_SLOT", "PGSD_B200_SLOT_BITS",
+KNOBS = ["PGSD_B200_SLOT_PER", "PGSD_B200_SLOT_UNIT", "PGSD_B200_SLOT_LAYOUT", "PGSD_B200_SLOT_CSTRIDE", "PGSD_B200_SLOT", "PGSD_B200_SLOT_BITS",
          "PGSD_B200_SLOT_TILE", "PGSD_B200_SLOT_BULK", "PGSD_B200_CLUSTER", "PGSD_B200_CLUSTER_TILE", "PGSD_B200_CLUSTER_THREADS",
          "PGSD_B200_CLUSTER_AGG", "PGSD_B200_CLUSTER_BITS"]
 VARIANTS = [
     ("general path", {"PGSD_B200_SLOT": "0"}),
     ("slot path", {"PGSD_B200_CLUSTER": "0"}),
+    ("slot per 4", {"PGSD_B200_SLOT_PER": "4"}),
+    ("slot per 1", {"PGSD_B200_SLOT_PER": "1"}),
+    ("slot per 2 t2048", {"PGSD_B200_SLOT_PER": "2", "PGSD_B200_SLOT_TILE": "2048"}),
+    ("slot per 4 t2048", {"PGSD_B200_SLOT_PER": "4", "PGSD_B200_SLOT_TILE": "2048"}),
+    ("slot per 2 t512", {"PGSD_B200_SLOT_PER": "2", "PGSD_B200_SLOT_TILE": "512"}),
+    ("slot per 4 t512", {"PGSD_B200_SLOT_PER": "4", "PGSD_B200_SLOT_TILE": "512"}),
     ("cluster default", {}),
     ("cluster t4096/512", {"PGSD_B200_CLUSTER_TILE": "4096", "PGSD_B200_CLUSTER_THREADS": "512"}),
     ("cluster t2048/512", {"PGSD_B200_CLUSTER_TILE": "2048", "PGSD_B200_CLUSTER_THREADS": "512"}),
