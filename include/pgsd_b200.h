@@ -237,7 +237,7 @@ int pgsd_b200_file_stage_ceiling(const char* path, uint64_t off, uint64_t bytes,
    pgsd_read_chunk, pgsd.c:2436-2537, is one blocking MPI_File_read_at per call): after three equally sized reads
    at a constant file stride the next two ranges are fetched into device staging buffers in the background.
    Counters since the library was loaded: calls served from staging, ranges fetched ahead, fetched ranges never
-   used.  PGSD_B200_READ_AHEAD=0 switches the mechanism off. */
+   used.  Opt-in: PGSD_B200_READ_AHEAD=1 (read per call). */
 int pgsd_b200_read_ahead_stats(uint64_t* hits, uint64_t* issued, uint64_t* dropped);
 /* Device self-tests of failure paths that valid inputs never reach.  which = 0: a kernel waits on an mbarrier
    whose bulk copy never arrives; returns 0 when the bounded wait gave up and reported it (the reorder kernels'

@@ -1365,7 +1365,9 @@ static int read_file_to_device_now(int fd, void* dev_dst, uint64_t bytes, uint64
 // staging buffers; a call that finds its range there only pays a device-to-device copy.  Only for read-only
 // handles; every open / close of a handle drops what was fetched, and a file whose size or mtime changed is not served
 // from staging (chunks of a GSD file are never rewritten in place, so a stale range needs an outside writer that
-// replaces the file between two reads of one handle).  PGSD_B200_READ_AHEAD=0 switches it off.
+// replaces the file between two reads of one handle).  OPT-IN: PGSD_B200_READ_AHEAD=1.  It is worth 5-8 % on
+// back-to-back reads (the reader threads are bound by the host's page-cache copy either way); its point is to overlap
+// the next read with what the caller does in between.
 namespace
     {
 constexpr int AHEAD_SLOTS = 3;
@@ -1383,7 +1385,6 @@ struct Ahead
     std::condition_variable cv_work, cv_done;
     std::thread th;
     bool running = false, stop = false;
-    int enabled = -1;
     int fd = -1; // our own descriptor of the file being read ahead
     dev_t dev = 0;
     ino_t ino = 0;
@@ -1398,6 +1399,7 @@ struct Ahead
     uint64_t hits = 0, issued = 0, dropped = 0;
     };
 Ahead g_ah;
+std::mutex g_ah_front; // serialises the callers of the read-ahead front end (taken before g_ah.mu; never by the worker)
 
 void ahead_main()
     {
@@ -1439,7 +1441,7 @@ void ahead_forget(std::unique_lock<std::mutex>& lk)
     for (AheadSlot& x : g_ah.slot)
         if (x.state == AH_QUEUED)
             x.state = AH_FREE;
-    g_ah.cv_done.wait(lk, [] {
+    const bool idle = g_ah.cv_done.wait_for(lk, std::chrono::seconds(60), [] {
         for (AheadSlot& x : g_ah.slot)
             if (x.state == AH_RUNNING || x.state == AH_COPYING)
                 return false;
@@ -1449,9 +1451,10 @@ void ahead_forget(std::unique_lock<std::mutex>& lk)
         {
         if (x.state == AH_READY)
             g_ah.dropped++;
-        x.state = AH_FREE;
+        if (x.state != AH_RUNNING && x.state != AH_COPYING)
+            x.state = AH_FREE;
         }
-    if (g_ah.fd >= 0)
+    if (g_ah.fd >= 0 && idle) // a read that is still running keeps its descriptor (leaked rather than closed under it)
         close(g_ah.fd);
     g_ah.fd = -1;
     g_ah.have_last = false;
@@ -1493,6 +1496,7 @@ bool ahead_same_file(const struct stat& st)
 
 void dev_read_ahead_reset()
     {
+    std::lock_guard<std::mutex> front(g_ah_front);
     std::unique_lock<std::mutex> lk(g_ah.mu);
     if (g_ah.fd >= 0)
         ahead_forget(lk);
@@ -1516,15 +1520,16 @@ int dev_read_file_to_device(int fd, void* dev_dst, uint64_t bytes, uint64_t file
         return rc;
     if (bytes == 0)
         return 0;
-    if (g_ah.enabled < 0)
-        {
-        const char* e = getenv("PGSD_B200_READ_AHEAD");
-        g_ah.enabled = (e && e[0] == '0') ? 0 : 1;
-        }
+    // opt-in (PGSD_B200_READ_AHEAD=1, read per call): see the note above
+    const char* ea = getenv("PGSD_B200_READ_AHEAD");
+    const bool enabled = ea != nullptr && ea[0] == '1';
     struct stat st;
-    if (!read_only || !g_ah.enabled || bytes < AHEAD_MIN_BYTES || bytes > AHEAD_MAX_BYTES || fstat(fd, &st) != 0)
+    if (!read_only || !enabled || bytes < AHEAD_MIN_BYTES || bytes > AHEAD_MAX_BYTES || fstat(fd, &st) != 0)
         return read_file_to_device_now(fd, dev_dst, bytes, file_off);
 
+    // one caller at a time from here on: a second thread (pgsd.hoomd's frame prefetch next to the main thread) must
+    // not drop or recycle a fetched range the first one is waiting for
+    std::lock_guard<std::mutex> front(g_ah_front);
     bool served = false;
         {
         std::unique_lock<std::mutex> lk(g_ah.mu);
@@ -1544,7 +1549,13 @@ int dev_read_file_to_device(int fd, void* dev_dst, uint64_t bytes, uint64_t file
                 hit = &x;
         if (hit)
             {
-            g_ah.cv_done.wait(lk, [&] { return hit->state == AH_READY || hit->state == AH_FAILED; });
+            // bounded: whatever goes wrong with the worker, the caller falls back to reading the range itself
+            g_ah.cv_done.wait_for(lk, std::chrono::seconds(5), [&] { return hit->state == AH_READY || hit->state == AH_FAILED; });
+            if (hit->state != AH_READY && hit->state != AH_FAILED)
+                hit = nullptr; // still queued or being read: left to the worker, dropped by a later call
+            }
+        if (hit)
+            {
             if (hit->state == AH_READY)
                 {
                 if (g_ah.st == nullptr && cudaStreamCreateWithFlags(&g_ah.st, cudaStreamNonBlocking) != cudaSuccess)

@@ -223,11 +223,12 @@ def _read_ahead_stats():
     return h.value, i.value, d.value
 
 
-def test_read_ahead_serves_constant_stride_reads(tmp_path):
+def test_read_ahead_serves_constant_stride_reads(tmp_path, monkeypatch):
     """Partitioned reads into device memory (the reference's benchmark-read pattern,
     benchmark-read.cc:46-120): equally sized reads at a constant file stride are fetched ahead into device staging.
     Every read must return the file's bytes whatever the access order, the staging must actually be used for the
     sequential orders, and a file replaced under the same name must never be served from ranges fetched before."""
+    monkeypatch.setenv("PGSD_B200_READ_AHEAD", "1")   # opt-in
     n, keys, frames = 96 * 1024, 3, 14            # 768 KiB per float64 chunk
     path = str(tmp_path / "ahead.gsd")
 
@@ -272,8 +273,9 @@ def test_read_ahead_serves_constant_stride_reads(tmp_path):
     assert issued >= hits and dropped <= issued
 
 
-def test_read_ahead_two_files_interleaved(tmp_path):
+def test_read_ahead_two_files_interleaved(tmp_path, monkeypatch):
     """Two read-only handles read alternately: the staging follows one file at a time and never mixes them up."""
+    monkeypatch.setenv("PGSD_B200_READ_AHEAD", "1")
     n, frames = 80 * 1024, 10
     rng = np.random.default_rng(9)
     paths, data = [], []
