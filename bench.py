@@ -1088,6 +1088,11 @@ def main():
                     help="development: run only the distributed-reorder leg and print its object")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    # A run of this file takes 2-4 minutes.  Should a leg ever stall (a rank waiting for another one), do not sit on
+    # the box until somebody else's limit strikes: after PGSD_BENCH_WATCHDOG_S seconds (default 1500) every thread's
+    # Python stack goes to stderr and the process exits with status 1 (torchrun then ends the other ranks).
+    import faulthandler
+    faulthandler.dump_traceback_later(float(os.environ.get("PGSD_BENCH_WATCHDOG_S", "1500")), exit=True)
     ncores = os.cpu_count() or 1
     bdir = bench_dir()
     common_cfg = {"workload": f"config 3: one {args.particles}-particle HOOMD-schema frame per step "
