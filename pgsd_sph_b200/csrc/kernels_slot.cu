@@ -31,8 +31,10 @@
 // of its ballot ranking.  When a duplicate key is found (flag), nothing of the result is trusted: the
 // caller falls back to the stable general path of kernels_sort.cu.
 //
-// Measured on B200, 16 Mi particles (profiles/README.md, r2): place 0.215 ms = 0.95 of the measured HBM
-// copy rate; scatter 0.50 ms, which decomposes (round-1 timing experiments, profiles/r2_time_slot_scatter_decomposition.txt) into
+// Measured on B200, 16 Mi particles: place 0.21 ms = 0.98 of the measured HBM copy rate; scatter 0.43-0.44 ms with
+// 512 threads per 1024-row tile (2 rows per thread, 4 CTAs = 64 warps per SM, 196 KB carve-out; profiles/r4_*: the
+// source-level ncu capture showed 41 % of the stall samples on the first use of an atomic's result at 50 % occupancy).
+// With 256 threads (profiles/README.md, r2) it was 0.50 ms, which decomposes (round-1 timing experiments, profiles/r2_time_slot_scatter_decomposition.txt) into
 // staging 0.12 + cursor atomics 0.16-0.20 + record stores 0.11 (+ 0.17 when they go to their scattered
 // places) -- additive although no unit is above 35 % busy in ncu: DRAM spends its time opening rows for the
 // write-backs, not transferring.  Tried without gain: a persistent double-buffered variant that overlaps
@@ -40,7 +42,11 @@
 // 256-byte cursor strides (+-3 %), tiles of 512 / 2048 rows (+-5 %); and a separate kernel that only takes the
 // positions (keys -> atomics -> 4 bytes per row; 0.16 ms = the L2's ~100 G atomics/s) with an atomic-free
 // scatter after it: 0.82 ms, because records then no longer arrive in position order and half-filled lines
-// are evicted and fetched again (DRAM 1.34 GB read / 0.99 GB written instead of 0.74 / 0.67).
+// are evicted and fetched again (DRAM 1.34 GB read / 0.99 GB written instead of 0.74 / 0.67).  Round 2, also without
+// gain: batched atomics, a fifth CTA per SM / 228 KB carve-out, a kernel specialised for
+// the 40-byte row with a third of the instructions, staging gaps without bank conflicts, a software-pipelined
+// persistent kernel.  tools/atomic_overlap_bench.cu: a coalesced copy of the same bytes with one cursor atomic per
+// row takes 0.30 ms -- the floor of this pass.
 //
 // Distributed (one frame partitioned over the ranks, pgsd_b200_reorder_distributed, bottom of this file): the same
 // kernels on each owner's share, fed by k6_part_scatter (records appended to the owner's inbox in peer memory as
