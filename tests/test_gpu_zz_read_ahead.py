@@ -1,0 +1,94 @@
+"""GPU tests of the opt-in read-ahead of partitioned reads into device memory (PGSD_B200_READ_AHEAD=1; device.cu,
+DESIGN.md section 4a).  Kept in a file of their own that sorts last: the feature is off by default."""
+import numpy as np
+import pytest
+
+from pgsd_sph_b200 import fl
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def cuda(lib):
+    assert lib.pgsd_b200_cuda_available() == 1, "no CUDA device: the device path has no CPU fallback"
+
+
+def _read_ahead_stats():
+    import ctypes as C
+    from pgsd_sph_b200 import _lib
+    h, i, d = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    _lib.load().pgsd_b200_read_ahead_stats(C.byref(h), C.byref(i), C.byref(d))
+    return h.value, i.value, d.value
+
+
+def test_read_ahead_serves_constant_stride_reads(tmp_path, monkeypatch):
+    """Partitioned reads into device memory (the reference's benchmark-read pattern,
+    benchmark-read.cc:46-120): equally sized reads at a constant file stride are fetched ahead into device staging.
+    Every read must return the file's bytes whatever the access order, the staging must actually be used for the
+    sequential orders, and a file replaced under the same name must never be served from ranges fetched before."""
+    monkeypatch.setenv("PGSD_B200_READ_AHEAD", "1")   # opt-in
+    n, keys, frames = 96 * 1024, 3, 14            # 768 KiB per float64 chunk
+    path = str(tmp_path / "ahead.gsd")
+
+    def write(seed):
+        rng = np.random.default_rng(seed)
+        data = {(i, k): rng.standard_normal(n) for i in range(frames) for k in range(keys)}
+        with fl.open(path, 'w', 'pgsd-b200', 'benchmark', [1, 0]) as f:
+            for i in range(frames):
+                for k in range(keys):
+                    f.write_chunk(f"q/{k}", data[i, k])
+                f.end_frame()
+        return data
+
+    data = write(1)
+    order = [(i, k) for i in range(frames) for k in range(keys)]
+    h0 = _read_ahead_stats()[0]
+    with fl.open(path, 'r') as f:
+        for i, k in order:                                          # file order: stride = one chunk
+            a = f.read_chunk(i, f"q/{k}", device=True)
+            assert a.to_numpy().tobytes() == data[i, k].tobytes(), (i, k)
+        h1 = _read_ahead_stats()[0]
+        assert h1 - h0 >= len(order) - 4                            # all but the reads that establish the pattern
+        lo, rows = n // 2 + 1000, n // 2 - 1000                      # a rank's row slice of every chunk, one key
+        for i in range(frames):
+            a = f.read_chunk(i, "q/1", N=rows, M=1, offset=lo, r_all=True, device=True)
+            assert a.to_numpy().tobytes() == data[i, 1][lo:lo + rows].tobytes(), i
+        h2 = _read_ahead_stats()[0]
+        assert h2 - h1 >= frames - 4
+        for i, k in reversed(order):                                # negative stride
+            assert f.read_chunk(i, f"q/{k}", device=True).to_numpy().tobytes() == data[i, k].tobytes(), (i, k)
+        rng = np.random.default_rng(5)
+        for j in rng.permutation(len(order)):                       # no pattern: direct reads, stale fetches dropped
+            i, k = order[j]
+            assert f.read_chunk(i, f"q/{k}", device=True).to_numpy().tobytes() == data[i, k].tobytes(), (i, k)
+        for i, k in order[:9]:                                      # leave fetched ranges behind ...
+            f.read_chunk(i, f"q/{k}", device=True)
+    data2 = write(2)                                                # ... and replace the file: same name, same sizes
+    with fl.open(path, 'r') as f:
+        for i, k in order:
+            assert f.read_chunk(i, f"q/{k}", device=True).to_numpy().tobytes() == data2[i, k].tobytes(), (i, k)
+    hits, issued, dropped = _read_ahead_stats()
+    assert issued >= hits and dropped <= issued
+
+
+def test_read_ahead_two_files_interleaved(tmp_path, monkeypatch):
+    """Two read-only handles read alternately: the staging follows one file at a time and never mixes them up."""
+    monkeypatch.setenv("PGSD_B200_READ_AHEAD", "1")
+    n, frames = 80 * 1024, 10
+    rng = np.random.default_rng(9)
+    paths, data = [], []
+    for j in range(2):
+        p = str(tmp_path / f"f{j}.gsd")
+        d = [rng.standard_normal(n).astype(np.float32).reshape(n // 4, 4) for _ in range(frames)]
+        with fl.open(p, 'w', 'pgsd-b200', 'benchmark', [1, 0]) as f:
+            for a in d:
+                f.write_chunk("x", a)
+                f.end_frame()
+        paths.append(p)
+        data.append(d)
+    with fl.open(paths[0], 'r') as f0, fl.open(paths[1], 'r') as f1:
+        for i in range(frames):
+            assert f0.read_chunk(i, "x", device=True).to_numpy().tobytes() == data[0][i].tobytes()
+            assert f1.read_chunk(i, "x", device=True).to_numpy().tobytes() == data[1][i].tobytes()
+        for i in range(frames):                                     # then one of them alone: the pattern is found again
+            assert f1.read_chunk(i, "x", device=True).to_numpy().tobytes() == data[1][i].tobytes()
