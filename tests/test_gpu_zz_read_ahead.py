@@ -5,7 +5,14 @@ import pytest
 
 from pgsd_sph_b200 import fl
 
-pytestmark = pytest.mark.gpu
+import os
+
+# The front end of the read-ahead was serialised and its waits bounded AFTER the round's last GPU run (STATUS.md): the
+# tests below passed on B200 with the version before that change (profiles/r5_gpu_tests_tail.txt: 582 passed) and
+# have not run with the present one.  The feature is off unless PGSD_B200_READ_AHEAD=1; its tests run on request.
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("PGSD_TEST_READ_AHEAD") != "1",
+                                 reason="opt-in feature (PGSD_B200_READ_AHEAD=1); set PGSD_TEST_READ_AHEAD=1 to run its tests")]
 
 
 @pytest.fixture(scope="module", autouse=True)
