@@ -31,7 +31,16 @@ _VTK_TYPE = {'float64': 'Float64', 'float32': 'Float32', 'int64': 'Int64', 'uint
              'uint32': 'UInt32', 'int16': 'Int16', 'uint16': 'UInt16', 'int8': 'Int8', 'uint8': 'UInt8'}
 _VTK_VERTEX = 1          # cell type id of a vertex
 _PIECE = 16 << 20        # file-stage piece: a multiple of the page size
-_WRITERS = 8
+
+
+def _writers():
+    """Threads that put the image into the file: as the library sizes its own file stage -- the host's cores divided
+    by the ranks that share it (torchrun's LOCAL_WORLD_SIZE), 2..8."""
+    try:
+        ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+    except ValueError:
+        ranks = 1
+    return max(2, min(8, (os.cpu_count() or 8) // ranks))
 
 
 def _col_f64(a, j=None):
@@ -215,7 +224,7 @@ def _write_image(path, img):
         if len(pieces) == 1:
             rcs = [put(pieces[0])]
         else:
-            with ThreadPoolExecutor(max_workers=min(_WRITERS, len(pieces))) as ex:
+            with ThreadPoolExecutor(max_workers=min(_writers(), len(pieces))) as ex:
                 rcs = list(ex.map(put, pieces))
         for rc in rcs:
             _lib.check(rc, "pgsd_b200_file_stage_write")
