@@ -239,6 +239,11 @@ int pgsd_b200_file_stage_ceiling(const char* path, uint64_t off, uint64_t bytes,
    Counters since the library was loaded: calls served from staging, ranges fetched ahead, fetched ranges never
    used.  Opt-in: PGSD_B200_READ_AHEAD=1 (read per call). */
 int pgsd_b200_read_ahead_stats(uint64_t* hits, uint64_t* issued, uint64_t* dropped);
+/* The same read-ahead state machine on HOST memory (staging = malloc, a read = pread), always on: for the CPU
+   test-suite, which reads files through it from several threads (tests/test_read_ahead_host.py). */
+int pgsd_b200_read_ahead_host_read(int fd, void* host_dst, uint64_t bytes, uint64_t off);
+int pgsd_b200_read_ahead_host_reset(void);
+int pgsd_b200_read_ahead_host_stats(uint64_t* hits, uint64_t* issued, uint64_t* dropped);
 /* Device self-tests of failure paths that valid inputs never reach.  which = 0: a kernel waits on an mbarrier
    whose bulk copy never arrives; returns 0 when the bounded wait gave up and reported it (the reorder kernels'
    "a bulk copy did not complete" path), > 0 otherwise. */

@@ -202,6 +202,9 @@ SIGNATURES = {
     "pgsd_b200_selftest": (_i, [_i]),
     "pgsd_b200_file_stage_write": (_i, [_i, _vp, _u64, _u64, _i]),
     "pgsd_b200_read_ahead_stats": (_i, [C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64)]),
+    "pgsd_b200_read_ahead_host_read": (_i, [_i, _vp, _u64, _u64]),
+    "pgsd_b200_read_ahead_host_reset": (_i, []),
+    "pgsd_b200_read_ahead_host_stats": (_i, [C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64)]),
     "pgsd_b200_file_stage_ceiling": (_i, [C.c_char_p, _u64, _u64, C.POINTER(C.c_double), C.POINTER(_i), C.POINTER(_i)]),
 }
 

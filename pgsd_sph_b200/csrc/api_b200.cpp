@@ -5,11 +5,14 @@
 #include "comm.h"
 #include "device.h"
 #include "file_stage.h"
+#include "read_ahead.h"
 
 #include <fcntl.h>
 #include <unistd.h>
 #include "file_internal.h"
 
+#include <cerrno>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -394,6 +397,57 @@ int pgsd_b200_file_stage_ceiling(const char* path, uint64_t off, uint64_t bytes,
 int pgsd_b200_read_ahead_stats(uint64_t* hits, uint64_t* issued, uint64_t* dropped)
     {
     dev_read_ahead_stats(hits, issued, dropped);
+    return PGSD_SUCCESS;
+    }
+
+// The same state machine on host memory (read_ahead.cpp has no CUDA in it): what the CPU suite hammers from several
+// threads.  Staging = malloc, a read = pread, the copy out of staging = memcpy.
+namespace
+    {
+bool hra_read_now(int fd, void* dst, uint64_t bytes, uint64_t off)
+    {
+    uint64_t got = 0;
+    while (got < bytes)
+        {
+        const ssize_t k = pread(fd, (char*)dst + got, bytes - got, (off_t)(off + got));
+        if (k < 0 && errno == EINTR)
+            continue;
+        if (k <= 0)
+            return false;
+        got += (uint64_t)k;
+        }
+    return true;
+    }
+bool hra_alloc(void** p, uint64_t bytes)
+    {
+    *p = malloc(bytes);
+    return *p != nullptr;
+    }
+void hra_release(void* p) { free(p); }
+bool hra_copy(void* dst, const void* src, uint64_t bytes)
+    {
+    memcpy(dst, src, bytes);
+    return true;
+    }
+ReadAhead g_host_ra(ReadAheadOps { hra_read_now, hra_alloc, hra_release, hra_copy, nullptr });
+    } // namespace
+
+int pgsd_b200_read_ahead_host_read(int fd, void* host_dst, uint64_t bytes, uint64_t off)
+    {
+    if (fd < 0 || (bytes > 0 && host_dst == nullptr))
+        return PGSD_ERROR_INVALID_ARGUMENT;
+    if (bytes == 0)
+        return PGSD_SUCCESS;
+    return g_host_ra.read(fd, host_dst, bytes, off) ? PGSD_SUCCESS : PGSD_ERROR_IO;
+    }
+int pgsd_b200_read_ahead_host_reset(void)
+    {
+    g_host_ra.reset();
+    return PGSD_SUCCESS;
+    }
+int pgsd_b200_read_ahead_host_stats(uint64_t* hits, uint64_t* issued, uint64_t* dropped)
+    {
+    g_host_ra.stats(hits, issued, dropped);
     return PGSD_SUCCESS;
     }
 

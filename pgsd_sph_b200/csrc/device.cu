@@ -9,6 +9,7 @@
 // 1162,2157,2242): one ncclAllGather of the frame's u64 size vector + a device scan.
 #include "device_internal.h"
 #include "file_stage.h"
+#include "read_ahead.h"
 
 #include <nvtx3/nvToolsExt.h> // header-only; ranges cost nothing unless a profiler (nsys) is attached
 #include <nccl.h> // types only; the library is dlopen()ed so that CPU-only hosts can load us
@@ -1362,156 +1363,48 @@ static int read_file_to_device_now(int fd, void* dev_dst, uint64_t bytes, uint64
 // field over the frames of a trajectory).  One such call costs the wake-up of the reader threads + the page-cache copy
 // + the tail of the H2D, and nothing overlaps the caller's own work between calls.  After three reads with the same
 // size and stride the next two are fetched ahead by a worker (same reader threads, same pinned pieces) into device
-// staging buffers; a call that finds its range there only pays a device-to-device copy.  Only for read-only
-// handles; every open / close of a handle drops what was fetched, and a file whose size or mtime changed is not served
-// from staging (chunks of a GSD file are never rewritten in place, so a stale range needs an outside writer that
-// replaces the file between two reads of one handle).  OPT-IN: PGSD_B200_READ_AHEAD=1.  It is worth 5-8 % on
-// back-to-back reads (the reader threads are bound by the host's page-cache copy either way); its point is to overlap
-// the next read with what the caller does in between.
+// staging buffers; a call that finds its range there only pays a device-to-device copy.  The state machine is
+// read_ahead.cpp (no CUDA in it: the CPU suite drives it with host memory from several threads); here are its
+// operations on device memory.  Only for read-only handles; every open / close of a handle drops what was fetched,
+// and a file whose size or mtime changed is not served from staging (chunks of a GSD file are never rewritten in
+// place, so a stale range needs an outside writer that replaces the file between two reads of one handle).
+// OPT-IN: PGSD_B200_READ_AHEAD=1.  It is worth 5-8 % on back-to-back reads (the reader threads are bound by the
+// host's page-cache copy either way); its point is to overlap the next read with what the caller does in between.
 namespace
     {
-constexpr int AHEAD_SLOTS = 3;
-constexpr uint64_t AHEAD_MIN_BYTES = 256ull << 10, AHEAD_MAX_BYTES = 64ull << 20;
-enum AheadState { AH_FREE = 0, AH_QUEUED, AH_RUNNING, AH_READY, AH_FAILED, AH_COPYING };
-struct AheadSlot
+bool ra_read_now(int fd, void* dst, uint64_t bytes, uint64_t off) { return read_file_to_device_now(fd, dst, bytes, off) == 0; }
+bool ra_alloc(void** p, uint64_t bytes)
     {
-    uint64_t off = 0, bytes = 0, cap = 0, seq = 0;
-    void* dev = nullptr;
-    int state = AH_FREE;
-    };
-struct Ahead
-    {
-    std::mutex mu;
-    std::condition_variable cv_work, cv_done;
-    std::thread th;
-    bool running = false, stop = false;
-    int fd = -1; // our own descriptor of the file being read ahead
-    dev_t dev = 0;
-    ino_t ino = 0;
-    int64_t size = 0;
-    struct timespec mtime = { 0, 0 };
-    bool have_last = false;
-    uint64_t last_off = 0, last_bytes = 0, seq = 0;
-    int64_t stride = 0;
-    int streak = 0;
-    AheadSlot slot[AHEAD_SLOTS];
-    cudaStream_t st = nullptr;
-    uint64_t hits = 0, issued = 0, dropped = 0;
-    };
-Ahead g_ah;
-std::mutex g_ah_front; // serialises the callers of the read-ahead front end (taken before g_ah.mu; never by the worker)
-
-void ahead_main()
-    {
-    cudaSetDevice(g.device);
-    for (;;)
-        {
-        AheadSlot* s = nullptr;
-        int fd = -1;
-            {
-            std::unique_lock<std::mutex> lk(g_ah.mu);
-            g_ah.cv_work.wait(lk, [&] {
-                if (g_ah.stop)
-                    return true;
-                for (AheadSlot& x : g_ah.slot)
-                    if (x.state == AH_QUEUED)
-                        return true;
-                return false;
-            });
-            if (g_ah.stop)
-                return;
-            for (AheadSlot& x : g_ah.slot)
-                if (x.state == AH_QUEUED && (s == nullptr || x.seq < s->seq))
-                    s = &x;
-            s->state = AH_RUNNING;
-            fd = g_ah.fd;
-            }
-        const bool ok = read_file_to_device_now(fd, s->dev, s->bytes, s->off) == 0;
-            {
-            std::lock_guard<std::mutex> lk(g_ah.mu);
-            s->state = ok ? AH_READY : AH_FAILED;
-            }
-        g_ah.cv_done.notify_all();
-        }
-    }
-
-// forget the file: nothing queued, nothing running, descriptor closed (buffers stay for the next file)
-void ahead_forget(std::unique_lock<std::mutex>& lk)
-    {
-    for (AheadSlot& x : g_ah.slot)
-        if (x.state == AH_QUEUED)
-            x.state = AH_FREE;
-    const bool idle = g_ah.cv_done.wait_for(lk, std::chrono::seconds(60), [] {
-        for (AheadSlot& x : g_ah.slot)
-            if (x.state == AH_RUNNING || x.state == AH_COPYING)
-                return false;
+    if (cudaMalloc(p, bytes) == cudaSuccess)
         return true;
-    });
-    for (AheadSlot& x : g_ah.slot)
-        {
-        if (x.state == AH_READY)
-            g_ah.dropped++;
-        if (x.state != AH_RUNNING && x.state != AH_COPYING)
-            x.state = AH_FREE;
-        }
-    if (g_ah.fd >= 0 && idle) // a read that is still running keeps its descriptor (leaked rather than closed under it)
-        close(g_ah.fd);
-    g_ah.fd = -1;
-    g_ah.have_last = false;
-    g_ah.streak = 0;
+    cudaGetLastError();
+    *p = nullptr;
+    return false;
     }
-
-void ahead_stop()
+void ra_release(void* p) { cudaFree(p); }
+bool ra_copy(void* dst, const void* src, uint64_t bytes) // callers are serialised (ReadAhead::read)
     {
+    static cudaStream_t st = nullptr;
+    if (st == nullptr && cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess)
         {
-        std::unique_lock<std::mutex> lk(g_ah.mu);
-        if (!g_ah.running && g_ah.fd < 0 && g_ah.slot[0].dev == nullptr)
-            return;
-        ahead_forget(lk);
-        g_ah.stop = true;
+        st = nullptr;
+        cudaGetLastError();
+        return false;
         }
-    g_ah.cv_work.notify_all();
-    if (g_ah.running)
-        g_ah.th.join();
-    std::lock_guard<std::mutex> lk(g_ah.mu);
-    g_ah.running = false;
-    g_ah.stop = false;
-    for (AheadSlot& x : g_ah.slot)
-        {
-        if (x.dev)
-            cudaFree(x.dev);
-        x = AheadSlot();
-        }
-    if (g_ah.st)
-        cudaStreamDestroy(g_ah.st);
-    g_ah.st = nullptr;
+    if (cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st) == cudaSuccess && cudaStreamSynchronize(st) == cudaSuccess)
+        return true;
+    cudaGetLastError();
+    return false;
     }
-
-bool ahead_same_file(const struct stat& st)
-    {
-    return g_ah.fd >= 0 && st.st_dev == g_ah.dev && st.st_ino == g_ah.ino && (int64_t)st.st_size == g_ah.size
-           && st.st_mtim.tv_sec == g_ah.mtime.tv_sec && st.st_mtim.tv_nsec == g_ah.mtime.tv_nsec;
-    }
+void ra_thread_init() { cudaSetDevice(g.device); }
+ReadAhead g_ra(ReadAheadOps { ra_read_now, ra_alloc, ra_release, ra_copy, ra_thread_init });
+// its worker uses the reader pool: read_pool_stop() (atexit, dev_shutdown) stops it first
+const bool g_ra_hooked = (g_ra.at_worker_start(read_pool_atexit), true);
+void ahead_stop() { g_ra.stop(); }
     } // namespace
 
-void dev_read_ahead_reset()
-    {
-    std::lock_guard<std::mutex> front(g_ah_front);
-    std::unique_lock<std::mutex> lk(g_ah.mu);
-    if (g_ah.fd >= 0)
-        ahead_forget(lk);
-    }
-
-void dev_read_ahead_stats(uint64_t* hits, uint64_t* issued, uint64_t* dropped)
-    {
-    std::lock_guard<std::mutex> lk(g_ah.mu);
-    if (hits)
-        *hits = g_ah.hits;
-    if (issued)
-        *issued = g_ah.issued;
-    if (dropped)
-        *dropped = g_ah.dropped;
-    }
+void dev_read_ahead_reset() { g_ra.reset(); }
+void dev_read_ahead_stats(uint64_t* hits, uint64_t* issued, uint64_t* dropped) { g_ra.stats(hits, issued, dropped); }
 
 int dev_read_file_to_device(int fd, void* dev_dst, uint64_t bytes, uint64_t file_off, bool read_only)
     {
@@ -1520,153 +1413,10 @@ int dev_read_file_to_device(int fd, void* dev_dst, uint64_t bytes, uint64_t file
         return rc;
     if (bytes == 0)
         return 0;
-    // opt-in (PGSD_B200_READ_AHEAD=1, read per call): see the note above
-    const char* ea = getenv("PGSD_B200_READ_AHEAD");
-    const bool enabled = ea != nullptr && ea[0] == '1';
-    struct stat st;
-    if (!read_only || !enabled || bytes < AHEAD_MIN_BYTES || bytes > AHEAD_MAX_BYTES || fstat(fd, &st) != 0)
+    const char* ea = getenv("PGSD_B200_READ_AHEAD"); // opt-in, read per call
+    if (!read_only || ea == nullptr || ea[0] != '1')
         return read_file_to_device_now(fd, dev_dst, bytes, file_off);
-
-    // one caller at a time from here on: a second thread (pgsd.hoomd's frame prefetch next to the main thread) must
-    // not drop or recycle a fetched range the first one is waiting for
-    std::lock_guard<std::mutex> front(g_ah_front);
-    bool served = false;
-        {
-        std::unique_lock<std::mutex> lk(g_ah.mu);
-        if (!ahead_same_file(st))
-            {
-            ahead_forget(lk);
-            g_ah.fd = dup(fd);
-            g_ah.dev = st.st_dev;
-            g_ah.ino = st.st_ino;
-            g_ah.size = (int64_t)st.st_size;
-            g_ah.mtime = st.st_mtim;
-            }
-        // (1) fetched ahead?
-        AheadSlot* hit = nullptr;
-        for (AheadSlot& x : g_ah.slot)
-            if ((x.state == AH_QUEUED || x.state == AH_RUNNING || x.state == AH_READY) && x.off == file_off && x.bytes == bytes)
-                hit = &x;
-        if (hit)
-            {
-            // bounded: whatever goes wrong with the worker, the caller falls back to reading the range itself
-            g_ah.cv_done.wait_for(lk, std::chrono::seconds(5), [&] { return hit->state == AH_READY || hit->state == AH_FAILED; });
-            if (hit->state != AH_READY && hit->state != AH_FAILED)
-                hit = nullptr; // still queued or being read: left to the worker, dropped by a later call
-            }
-        if (hit)
-            {
-            if (hit->state == AH_READY)
-                {
-                if (g_ah.st == nullptr && cudaStreamCreateWithFlags(&g_ah.st, cudaStreamNonBlocking) != cudaSuccess)
-                    g_ah.st = nullptr;
-                hit->state = AH_COPYING; // nobody else matches or recycles it meanwhile
-                lk.unlock();
-                served = g_ah.st != nullptr
-                         && cudaMemcpyAsync(dev_dst, hit->dev, bytes, cudaMemcpyDeviceToDevice, g_ah.st) == cudaSuccess
-                         && cudaStreamSynchronize(g_ah.st) == cudaSuccess;
-                if (!served)
-                    cudaGetLastError();
-                lk.lock();
-                if (served)
-                    g_ah.hits++;
-                }
-            hit->state = AH_FREE;
-            g_ah.cv_done.notify_all();
-            }
-        // (2) the pattern: same size, same stride
-        if (g_ah.have_last && bytes == g_ah.last_bytes)
-            {
-            const int64_t d = (int64_t)file_off - (int64_t)g_ah.last_off;
-            if (d == g_ah.stride && d != 0)
-                g_ah.streak++;
-            else
-                {
-                g_ah.stride = d;
-                g_ah.streak = d != 0 ? 1 : 0;
-                }
-            }
-        else
-            {
-            g_ah.stride = 0;
-            g_ah.streak = 0;
-            }
-        g_ah.have_last = true;
-        g_ah.last_off = file_off;
-        g_ah.last_bytes = bytes;
-        // (3) what should be in flight now: the next two ranges of the pattern; everything else is dropped
-        uint64_t want[2] = { 0, 0 };
-        int nwant = 0;
-        if (g_ah.streak >= 2 && g_ah.fd >= 0)
-            for (int k = 1; k <= 2; k++)
-                {
-                const int64_t t = (int64_t)file_off + k * g_ah.stride;
-                if (t < 0 || (uint64_t)t + bytes > (uint64_t)g_ah.size)
-                    break;
-                want[nwant++] = (uint64_t)t;
-                }
-        for (AheadSlot& x : g_ah.slot)
-            {
-            if (x.state == AH_FREE || x.state == AH_RUNNING || x.state == AH_COPYING)
-                continue;
-            bool wanted = false;
-            for (int k = 0; k < nwant; k++)
-                wanted = wanted || (x.off == want[k] && x.bytes == bytes);
-            if (!wanted || x.state == AH_FAILED)
-                {
-                if (x.state == AH_READY)
-                    g_ah.dropped++;
-                x.state = AH_FREE;
-                }
-            }
-        bool queued = false;
-        for (int k = 0; k < nwant; k++)
-            {
-            bool have = false;
-            for (AheadSlot& x : g_ah.slot)
-                have = have || (x.state != AH_FREE && x.off == want[k] && x.bytes == bytes);
-            if (have)
-                continue;
-            AheadSlot* f = nullptr;
-            for (AheadSlot& x : g_ah.slot)
-                if (x.state == AH_FREE && f == nullptr)
-                    f = &x;
-            if (f == nullptr)
-                break;
-            if (f->cap < bytes)
-                {
-                if (f->dev)
-                    cudaFree(f->dev);
-                f->dev = nullptr;
-                f->cap = 0;
-                if (cudaMalloc(&f->dev, bytes) != cudaSuccess)
-                    {
-                    cudaGetLastError();
-                    break;
-                    }
-                f->cap = bytes;
-                }
-            f->off = want[k];
-            f->bytes = bytes;
-            f->seq = ++g_ah.seq;
-            f->state = AH_QUEUED;
-            g_ah.issued++;
-            queued = true;
-            }
-        if (queued)
-            {
-            if (!g_ah.running)
-                {
-                read_pool_atexit();
-                g_ah.th = std::thread(ahead_main);
-                g_ah.running = true;
-                }
-            g_ah.cv_work.notify_one();
-            }
-        }
-    if (served)
-        return 0;
-    return read_file_to_device_now(fd, dev_dst, bytes, file_off);
+    return g_ra.read(fd, dev_dst, bytes, file_off) ? 0 : -1;
     }
 
 // ------------------------------------------------------------------------------ K2
