@@ -6,7 +6,9 @@ scheme (arbitrary byte ranges mapped by several writers); `PGSD_STRESS_ITERS=200
 is the long run recorded under profiles/."""
 import ctypes as C
 import multiprocessing as mp
+import atexit
 import os
+import shutil
 import threading
 
 import numpy as np
@@ -39,6 +41,7 @@ def targets(tmp_path):
     if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK):
         d = os.path.join("/dev/shm", "pgsd_fs_%d_%s" % (os.getpid(), tmp_path.name))
         os.makedirs(d, exist_ok=True)
+        atexit.register(shutil.rmtree, d, True)   # tmp_path is pytest's to clean; this one is ours
         dirs.append(d)
     return dirs
 
